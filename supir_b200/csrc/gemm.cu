@@ -1,0 +1,557 @@
+// supir_b200 — K2/K3/K4 of SURVEY.md §2a: Linear, conv1x1 and conv3x3 (implicit GEMM) on tcgen05.
+//
+//   out[m, n] = epilogue( sum_k A[m, k] * W[n, k] )          bf16 x bf16 -> fp32 (TMEM) -> bf16/fp32
+//
+// Replaces, on the sampling path of the reference: nn.Linear (sgm/modules/attention.py:213-218,87,106,587,611),
+// nn.Conv2d 1x1 (openaimodel.py:317, SUPIR_v0.py:48,87, model.py:124-126,164-175) and nn.Conv2d 3x3 stride 1 pad 1
+// (openaimodel.py:263,300-307; SUPIR_v0.py:79,82-83; model.py:108-117 ...).
+//
+// Design (one persistent CTA per SM, 192 threads, warp-specialised):
+//   warp 0 lane 0 : TMA producer.  A tile = 128 rows x 64 k (bf16, 128B-swizzled), W tile = BN rows x 64 k.
+//                   GEMM mode: A is a 2-D tensor map over [M, K].
+//                   CONV mode: A is a 4-D tensor map over the NHWC activation [B, H, W, C]; the tile's 128 rows are a
+//                   TH x TW pixel patch and the k-loop runs over (tap, 64-channel chunk); the tap shift is applied to the
+//                   TMA coordinates, and TMA's out-of-bounds zero fill IS the conv padding (no im2col buffer).
+//   warp 1 lane 0 : tcgen05.mma issuer (UMMA 128 x BN x 16, accumulators in TMEM, double-buffered across tiles).
+//   warps 2..5    : epilogue. tcgen05.ld 32 columns at a time; +bias, +per-batch vector (timestep embedding),
+//                   SiLU / GEGLU, bf16 round, +residual, 64-byte-contiguous global stores.
+// Pipelines: smem full/empty ring (TMA <-> MMA) and TMEM full/empty (MMA <-> epilogue).
+#include "common.cuh"
+#include "supir_b200.h"
+
+#include <mutex>
+
+namespace supir {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;
+static constexpr int GEMM_THREADS = 192;
+
+struct GemmKernelParams {
+    int M, N, K;          // N = accumulator columns (before GEGLU halving)
+    int num_m_tiles, num_n_tiles, num_kb;
+    // conv mode
+    int conv;             // 0 gemm, 1 conv3x3
+    int H, W, Cin, TH, TW, tiles_x, tiles_y, kchunks;
+    // epilogue
+    const float* bias;
+    const float* rowvec;
+    int rows_per_batch;
+    int rowvec_ld;
+    const __nv_bfloat16* residual;
+    long long ldr;
+    int act;
+    void* out;
+    long long ldc;
+    int out_f32;
+    int n_out;            // valid output columns (N or N/2 for GEGLU)
+    uint32_t desc_hi;     // upper 32 bits of the shared-memory matrix descriptor (SBO / version / swizzle mode)
+    uint32_t desc_lbo;    // LBO field (bits 16..29 of the low word), pre-shifted
+    uint32_t idesc;       // tcgen05 instruction descriptor
+};
+
+template <int BN>
+struct GemmSmem {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmKernelParams p) {
+    using S = GemmSmem<BN>;
+    constexpr int STAGES = S::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * S::A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+    uint64_t* full_bar = bars;                    // [STAGES]
+    uint64_t* empty_bar = bars + STAGES;          // [STAGES]
+    uint64_t* tmem_full = bars + 2 * STAGES;      // [2]
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr, 2 * BN);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer =====================
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int mt = tile % p.num_m_tiles;
+                const int nt = tile / p.num_m_tiles;
+                int b = 0, y0 = 0, x0 = 0;
+                if (p.conv) {
+                    const int per_img = p.tiles_x * p.tiles_y;
+                    b = mt / per_img;
+                    const int r = mt % per_img;
+                    y0 = (r / p.tiles_x) * p.TH;
+                    x0 = (r % p.tiles_x) * p.TW;
+                }
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+                    if (p.conv) {
+                        const int tap = kb / p.kchunks;
+                        const int cc = kb - tap * p.kchunks;
+                        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                        tma_load_4d(smem_a + stage * S::A_BYTES, &tmA, &full_bar[stage], cc * BK, x0 + dx, y0 + dy, b);
+                        tma_load_2d(smem_b + stage * S::B_BYTES, &tmB, &full_bar[stage], tap * p.Cin + cc * BK,
+                                    nt * BN);
+                    } else {
+                        tma_load_2d(smem_a + stage * S::A_BYTES, &tmA, &full_bar[stage], kb * BK, mt * BM);
+                        tma_load_2d(smem_b + stage * S::B_BYTES, &tmB, &full_bar[stage], kb * BK, nt * BN);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===================== MMA issuer =====================
+            const uint32_t idesc = p.idesc;
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t dtemplate = ((uint64_t)p.desc_hi << 32) | p.desc_lbo;
+                    const uint64_t adesc = dtemplate | ((smem_u32(smem_a + stage * S::A_BYTES) >> 4) & 0x3FFF);
+                    const uint64_t bdesc = dtemplate | ((smem_u32(smem_b + stage * S::B_BYTES) >> 4) & 0x3FFF);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // advance 16 k-elements = 32 bytes inside the 128B swizzle atom: +2 in the (addr>>4) field
+                        umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+        const int row_in_tile = quad * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int mt = tile % p.num_m_tiles;
+            const int nt = tile / p.num_m_tiles;
+            // global row / validity
+            long long grow;
+            int batch_idx;
+            bool row_ok;
+            if (p.conv) {
+                const int per_img = p.tiles_x * p.tiles_y;
+                const int b = mt / per_img;
+                const int r = mt % per_img;
+                const int y = (r / p.tiles_x) * p.TH + row_in_tile / p.TW;
+                const int x = (r % p.tiles_x) * p.TW + row_in_tile % p.TW;
+                row_ok = (y < p.H) && (x < p.W);
+                grow = ((long long)b * p.H + y) * p.W + x;
+                batch_idx = b;
+            } else {
+                grow = (long long)mt * BM + row_in_tile;
+                row_ok = grow < p.M;
+                batch_idx = p.rows_per_batch > 0 ? (int)(grow / p.rows_per_batch) : 0;
+            }
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                const int n0 = nt * BN + c0;
+                if (n0 >= p.N) break;  // warp-uniform
+                uint32_t r[32];
+                tmem_ld_32x32(t_row + c0, r);
+                tmem_ld_wait();
+                if (row_ok) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    if (p.bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (n0 + j < p.N) v[j] += __ldg(p.bias + n0 + j);
+                    }
+                    if (p.rowvec) {
+                        const float* rv = p.rowvec + (long long)batch_idx * p.rowvec_ld + n0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (n0 + j < p.N) v[j] += __ldg(rv + j);
+                    }
+                    if (p.act == 2) {
+                        // GEGLU: accumulator columns come in groups of 32 = [16 value | 16 gate]
+                        const int o0 = (n0 >> 5) * 16;
+                        float o[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            o[j] = bf16_round(bf16_round(v[j]) * bf16_round(gelu_erf_f(bf16_round(v[16 + j]))));
+                        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + grow * p.ldc + o0;
+                        if (p.residual) {
+                            const __nv_bfloat16* rs = p.residual + grow * p.ldr + o0;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (o0 + j < p.n_out) o[j] += __bfloat162float(rs[j]);
+                        }
+                        if (o0 + 16 <= p.n_out && ((p.ldc & 7) == 0)) {
+                            uint4 q0, q1;
+                            q0.x = pack_bf16x2(o[0], o[1]);   q0.y = pack_bf16x2(o[2], o[3]);
+                            q0.z = pack_bf16x2(o[4], o[5]);   q0.w = pack_bf16x2(o[6], o[7]);
+                            q1.x = pack_bf16x2(o[8], o[9]);   q1.y = pack_bf16x2(o[10], o[11]);
+                            q1.z = pack_bf16x2(o[12], o[13]); q1.w = pack_bf16x2(o[14], o[15]);
+                            reinterpret_cast<uint4*>(dst)[0] = q0;
+                            reinterpret_cast<uint4*>(dst)[1] = q1;
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (o0 + j < p.n_out) dst[j] = __float2bfloat16_rn(o[j]);
+                        }
+                    } else {
+                        if (p.act == 1) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = silu_f(bf16_round(v[j]));
+                        }
+                        if (p.out_f32) {
+                            float* dst = reinterpret_cast<float*>(p.out) + grow * p.ldc + n0;
+                            if (p.residual) {
+                                const __nv_bfloat16* rs = p.residual + grow * p.ldr + n0;
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (n0 + j < p.N) v[j] += __bfloat162float(rs[j]);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (n0 + j < p.N) dst[j] = v[j];
+                        } else {
+                            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + grow * p.ldc + n0;
+                            const bool vec_ok = (n0 + 32 <= p.N) && ((p.ldc & 7) == 0) &&
+                                                ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+                            if (p.residual) {
+                                const __nv_bfloat16* rs = p.residual + grow * p.ldr + n0;
+                                if (vec_ok && ((p.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0)) {
+                                    const uint4* rq = reinterpret_cast<const uint4*>(rs);
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        const uint4 u = __ldg(rq + q);
+                                        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                                        for (int t = 0; t < 4; ++t) {
+                                            const float2 f = unpack_bf16x2(w[t]);
+                                            v[q * 8 + t * 2] = bf16_round(v[q * 8 + t * 2]) + f.x;
+                                            v[q * 8 + t * 2 + 1] = bf16_round(v[q * 8 + t * 2 + 1]) + f.y;
+                                        }
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j)
+                                        if (n0 + j < p.N) v[j] = bf16_round(v[j]) + __bfloat162float(rs[j]);
+                                }
+                            }
+                            if (vec_ok) {
+                                uint4* dq = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    uint4 u;
+                                    u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+                                    u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+                                    u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+                                    u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+                                    dq[q] = u;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (n0 + j < p.N) dst[j] = __float2bfloat16_rn(v[j]);
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * BN);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled get_encode_fn() {
+    static PFN_tmapEncodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_tmapEncodeTiled>(f);
+    });
+    return fn;
+}
+
+// rank-N bf16 tensor map with 128B swizzle; dims/strides innermost first; strides in ELEMENTS for dims 1..rank-1
+int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                   const uint32_t* box) {
+    PFN_tmapEncodeTiled fn = get_encode_fn();
+    if (!fn) return set_error(SUPIR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = 1;
+    }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_elems[i] * 2;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0)
+        return set_error(SUPIR_ERR_INVALID, "TMA base address %p is not 16-byte aligned", base);
+    for (int i = 0; i + 1 < rank; ++i)
+        if (gstr[i] % 16 != 0) return set_error(SUPIR_ERR_INVALID, "TMA stride %d (%llu B) not a multiple of 16", i,
+                                                 (unsigned long long)gstr[i]);
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(SUPIR_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return SUPIR_OK;
+}
+
+int device_sm_count() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+static int g_force_bn = 0;
+static long long g_desc_override = -1;   // debug: full 64-bit descriptor template (address bits zero), -1 = default
+static long long g_idesc_override = -1;  // debug: instruction descriptor, -1 = default
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmKernelParams p, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        SUPIR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              GemmSmem<BN>::TOTAL));
+        attr_set = true;
+    }
+    p.num_n_tiles = (p.N + BN - 1) / BN;
+    {
+        uint64_t dt = g_desc_override >= 0 ? (uint64_t)g_desc_override
+                                           : (((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61));
+        p.desc_hi = (uint32_t)(dt >> 32);
+        p.desc_lbo = (uint32_t)(dt & 0xFFFFFFFFu);
+        p.idesc = g_idesc_override >= 0 ? (uint32_t)g_idesc_override : umma_idesc_bf16(BM, BN);
+    }
+    const int tiles = p.num_m_tiles * p.num_n_tiles;
+    const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+    gemm_tcgen05_kernel<BN><<<grid, GEMM_THREADS, GemmSmem<BN>::TOTAL, st>>>(tmA, tmB, p);
+    count_launch();
+    SUPIR_CHECK_CUDA(cudaGetLastError());
+    return SUPIR_OK;
+}
+
+// choose the N tile: minimise (waves x per-tile cost); 256-wide tiles halve shared-memory traffic per flop.
+static int pick_bn(int m_tiles, int N, int force_bn) {
+    if (force_bn == 64 || force_bn == 128 || force_bn == 256) return force_bn;
+    const int sms = device_sm_count();
+    int best = 128;
+    double best_cost = 1e30;
+    const int cands[3] = {256, 128, 64};
+    for (int i = 0; i < 3; ++i) {
+        const int bn = cands[i];
+        if (bn > 64 && N <= bn / 2) continue;
+        const long long tiles = (long long)m_tiles * ((N + bn - 1) / bn);
+        const long long waves = (tiles + sms - 1) / sms;
+        // per-tile cost model: MMA time ~ bn, plus a fixed prologue/epilogue overhead; narrow tiles are smem-bound
+        const double tile_cost = bn * (bn == 256 ? 1.0 : (bn == 128 ? 1.1 : 1.35)) + 24.0;
+        const double cost = waves * tile_cost;
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+    }
+    return best;
+}
+
+
+static int run_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmKernelParams& p, cudaStream_t st) {
+    const int bn = pick_bn(p.num_m_tiles, p.N, g_force_bn);
+    if (bn == 256) return launch_gemm<256>(tmA, tmB, p, st);
+    if (bn == 128) return launch_gemm<128>(tmA, tmB, p, st);
+    return launch_gemm<64>(tmA, tmB, p, st);
+}
+
+static int fill_epilogue(GemmKernelParams& p, const supir_epilogue* ep, int N) {
+    p.bias = nullptr; p.rowvec = nullptr; p.rows_per_batch = 0; p.rowvec_ld = 0;
+    p.residual = nullptr; p.ldr = 0; p.act = 0; p.out_f32 = 0; p.n_out = N;
+    if (ep) {
+        p.bias = ep->bias;
+        p.rowvec = ep->rowvec;
+        p.rows_per_batch = ep->rows_per_batch;
+        p.rowvec_ld = ep->rowvec_ld > 0 ? ep->rowvec_ld : N;
+        p.residual = reinterpret_cast<const __nv_bfloat16*>(ep->residual);
+        p.ldr = ep->ldr;
+        p.act = ep->act;
+        p.out_f32 = ep->out_f32;
+        SUPIR_REQUIRE(p.act >= 0 && p.act <= 2, "epilogue act %d not in {0,1,2}", p.act);
+        if (p.act == 2) {
+            SUPIR_REQUIRE(N % 32 == 0, "GEGLU epilogue needs N %% 32 == 0 (got %d)", N);
+            SUPIR_REQUIRE(!p.out_f32, "GEGLU epilogue writes bf16 only");
+            p.n_out = N / 2;
+        }
+        if (p.residual) SUPIR_REQUIRE(p.ldr >= p.n_out, "residual ld %lld < %d", p.ldr, p.n_out);
+    }
+    return SUPIR_OK;
+}
+
+}  // namespace supir
+
+using namespace supir;
+
+extern "C" int supir_debug_set_umma_descriptors(long long smem_desc_template, long long idesc) {
+    g_desc_override = smem_desc_template;
+    g_idesc_override = idesc;
+    return SUPIR_OK;
+}
+
+extern "C" int supir_set_gemm_tile_n(int bn) {
+    g_force_bn = bn;
+    return SUPIR_OK;
+}
+
+extern "C" int supir_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldc,
+                               int M, int N, int K, const supir_epilogue* ep, void* stream) {
+    SUPIR_REQUIRE(A && W && out, "supir_gemm_bf16: null pointer");
+    SUPIR_REQUIRE(M > 0 && N > 0 && K > 0, "supir_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
+    SUPIR_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "supir_gemm_bf16: K/lda/ldw must be multiples of 8");
+    SUPIR_REQUIRE(lda >= K && ldw >= K, "supir_gemm_bf16: leading dims smaller than K");
+    GemmKernelParams p{};
+    p.M = M; p.N = N; p.K = K;
+    p.num_m_tiles = (M + BM - 1) / BM;
+    p.num_kb = (K + BK - 1) / BK;
+    p.conv = 0;
+    int rc = fill_epilogue(p, ep, N);
+    if (rc) return rc;
+    SUPIR_REQUIRE(ldc >= p.n_out, "supir_gemm_bf16: ldc %lld < output columns %d", ldc, p.n_out);
+    p.out = out; p.ldc = ldc;
+    const int bn = pick_bn(p.num_m_tiles, N, g_force_bn);
+    CUtensorMap tmA, tmB;
+    {
+        const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+        const uint64_t str[1] = {(uint64_t)lda};
+        const uint32_t box[2] = {BK, BM};
+        rc = make_tmap_bf16(&tmA, A, 2, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+        const uint64_t str[1] = {(uint64_t)ldw};
+        const uint32_t box[2] = {BK, (uint32_t)bn};
+        rc = make_tmap_bf16(&tmB, W, 2, dims, str, box);
+        if (rc) return rc;
+    }
+    return run_gemm(tmA, tmB, p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int supir_conv3x3_bf16(const void* x, long long ldx, const void* Wp, void* out, long long ldc, int B, int H,
+                                  int Wd, int Cin, int Cout, const supir_epilogue* ep, void* stream) {
+    SUPIR_REQUIRE(x && Wp && out, "supir_conv3x3_bf16: null pointer");
+    SUPIR_REQUIRE(B > 0 && H > 0 && Wd > 0 && Cin > 0 && Cout > 0, "supir_conv3x3_bf16: bad shape");
+    SUPIR_REQUIRE(Cin % 8 == 0 && ldx % 8 == 0 && ldx >= Cin, "supir_conv3x3_bf16: Cin/ldx must be multiples of 8");
+    GemmKernelParams p{};
+    p.conv = 1;
+    p.H = H; p.W = Wd; p.Cin = Cin;
+    // pixel patch per tile: TH x TW = 128 pixels; pick the shape that wastes the fewest out-of-image pixels
+    {
+        const int cand[5] = {16, 8, 32, 64, 128};
+        long long best = -1;
+        int TW = 16;
+        for (int i = 0; i < 5; ++i) {
+            const int tw = cand[i], th = BM / tw;
+            const long long t = (long long)((Wd + tw - 1) / tw) * ((H + th - 1) / th);
+            if (best < 0 || t < best) { best = t; TW = tw; }
+        }
+        p.TW = TW; p.TH = BM / TW;
+    }
+    p.tiles_x = (Wd + p.TW - 1) / p.TW;
+    p.tiles_y = (H + p.TH - 1) / p.TH;
+    p.num_m_tiles = B * p.tiles_x * p.tiles_y;
+    p.kchunks = (Cin + BK - 1) / BK;
+    p.num_kb = 9 * p.kchunks;
+    p.M = B * H * Wd; p.N = Cout; p.K = 9 * Cin;
+    int rc = fill_epilogue(p, ep, Cout);
+    if (rc) return rc;
+    SUPIR_REQUIRE(ldc >= p.n_out, "supir_conv3x3_bf16: ldc %lld < output columns %d", ldc, p.n_out);
+    p.out = out; p.ldc = ldc;
+    const int bn = pick_bn(p.num_m_tiles, Cout, g_force_bn);
+    CUtensorMap tmA, tmB;
+    {
+        const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Wd, (uint64_t)H, (uint64_t)B};
+        const uint64_t str[3] = {(uint64_t)ldx, (uint64_t)ldx * Wd, (uint64_t)ldx * Wd * H};
+        const uint32_t box[4] = {BK, (uint32_t)p.TW, (uint32_t)p.TH, 1};
+        rc = make_tmap_bf16(&tmA, x, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t dims[2] = {(uint64_t)(9 * Cin), (uint64_t)Cout};
+        const uint64_t str[1] = {(uint64_t)(9 * Cin)};
+        const uint32_t box[2] = {BK, (uint32_t)bn};
+        rc = make_tmap_bf16(&tmB, Wp, 2, dims, str, box);
+        if (rc) return rc;
+    }
+    return run_gemm(tmA, tmB, p, reinterpret_cast<cudaStream_t>(stream));
+}

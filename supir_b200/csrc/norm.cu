@@ -1,0 +1,407 @@
+// supir_b200 — K1/K5/K13 of SURVEY.md §2a: GroupNorm(32) [+SiLU], LayerNorm, tiled-VAE cross-tile GroupNorm.
+// All HBM-bound: 128-bit loads/stores on channels-last bf16, fp32 math, fp64 cross-block sums.
+//
+// Reference call sites: GroupNorm32 (sgm/modules/diffusionmodules/util.py:258-276, eps 1e-5) in ResBlock
+// (openaimodel.py:260-264,295-308), ZeroSFT/ZeroCrossAttn (SUPIR/modules/SUPIR_v0.py:72,110,128-129);
+// attention.Normalize / VAE Normalize (attention.py:122-125, model.py:49-52, eps 1e-6); nn.LayerNorm
+// (attention.py:437-439); tiled VAE statistics merge (SUPIR/utils/tilevae.py:511-553, 599-648).
+#include "common.cuh"
+#include "supir_b200.h"
+
+namespace supir {
+
+// ---------------------------------------------------------------------------------------------
+// GroupNorm statistics: per (image, group) sum and sum of squares, accumulated in fp64.
+// Block = KP pixels x (C/8) channel-vectors; each thread keeps 8 channel accumulators for a strided subset of the
+// block's pixel chunk, then the block reduces to groups in shared memory and issues one fp64 atomicAdd per group.
+// ---------------------------------------------------------------------------------------------
+__global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int HW, int C, int G,
+                                int pixels_per_block, double* __restrict__ sums) {
+    extern __shared__ float sm[];  // [2][C]
+    const int cv_count = C >> 3;
+    const int kp = blockDim.x / cv_count;
+    const int cv = threadIdx.x % cv_count;
+    const int pl = threadIdx.x / cv_count;
+    const int b = blockIdx.y;
+    const int p0 = blockIdx.x * pixels_per_block;
+    const int p1 = min(p0 + pixels_per_block, HW);
+    float s[8], ss[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
+    if (pl < kp) {
+        const __nv_bfloat16* base = x + ((long long)b * HW) * ldx + cv * 8;
+        for (int p = p0 + pl; p < p1; p += kp) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (long long)p * ldx));
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float2 f = unpack_bf16x2(w[t]);
+                s[2 * t] += f.x; ss[2 * t] += f.x * f.x;
+                s[2 * t + 1] += f.y; ss[2 * t + 1] += f.y * f.y;
+            }
+        }
+    }
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    if (pl < kp) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            atomicAdd(&sm[cv * 8 + j], s[j]);
+            atomicAdd(&sm[C + cv * 8 + j], ss[j]);
+        }
+    }
+    __syncthreads();
+    const int cpg = C / G;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        double a = 0, q = 0;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+            a += sm[c];
+            q += sm[C + c];
+        }
+        atomicAdd(&sums[((long long)b * G + g) * 2], a);
+        atomicAdd(&sums[((long long)b * G + g) * 2 + 1], q);
+    }
+}
+
+// sums -> (mean, biased var) per (image, group)
+__global__ void gn_finalize_kernel(const double* __restrict__ sums, int n, double count, float* __restrict__ mean,
+                                   float* __restrict__ var) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double m = sums[2 * i] / count;
+    double v = sums[2 * i + 1] / count - m * m;
+    if (v < 0) v = 0;
+    mean[i] = (float)m;
+    var[i] = (float)v;
+}
+
+// tiled VAE: pixel-count-weighted average of per-tile mean AND var (the reference's approximation, tilevae.py:629-648)
+__global__ void gn_merge_tiles_kernel(const float* __restrict__ tile_mean, const float* __restrict__ tile_var,
+                                      const float* __restrict__ weights, int T, int n, float* __restrict__ mean,
+                                      float* __restrict__ var) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float m = 0.f, v = 0.f;
+    for (int t = 0; t < T; ++t) {  // same summation order as torch.sum over the tile dimension
+        m += tile_mean[(long long)t * n + i] * weights[t];
+        v += tile_var[(long long)t * n + i] * weights[t];
+    }
+    mean[i] = m;
+    var[i] = v;
+}
+
+// y = (x - mean) * rsqrt(var + eps) * gamma + beta [-> SiLU] ; bf16 in, bf16 out, channels-last
+__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y,
+                                long long ldy, int HW, int C, int G, const float* __restrict__ mean,
+                                const float* __restrict__ var, const double* __restrict__ sums, double count,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
+                                int pixels_per_block) {
+    extern __shared__ float sm[];  // scale[C], shift[C]
+    const int b = blockIdx.y;
+    const int cpg = C / G;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        float m, v;
+        if (sums) {
+            const double dm = sums[((long long)b * G + g) * 2] / count;
+            double dv = sums[((long long)b * G + g) * 2 + 1] / count - dm * dm;
+            if (dv < 0) dv = 0;
+            m = (float)dm; v = (float)dv;
+        } else {
+            m = mean[b * G + g]; v = var[b * G + g];
+        }
+        const float rstd = rsqrtf(v + eps);
+        const float sc = rstd * (gamma ? gamma[c] : 1.f);
+        sm[c] = sc;
+        sm[C + c] = (beta ? beta[c] : 0.f) - m * sc;
+    }
+    __syncthreads();
+    const int cv_count = C >> 3;
+    const int p0 = blockIdx.x * pixels_per_block;
+    const int p1 = min(p0 + pixels_per_block, HW);
+    const long long total = (long long)(p1 - p0) * cv_count;
+    for (long long i = threadIdx.x; i < total; i += blockDim.x) {
+        const int p = p0 + (int)(i / cv_count);
+        const int cv = (int)(i % cv_count);
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + ((long long)b * HW + p) * ldx + cv * 8));
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float2 f = unpack_bf16x2(w[t]);
+            const int c = cv * 8 + 2 * t;
+            float a = f.x * sm[c] + sm[C + c];
+            float d = f.y * sm[c + 1] + sm[C + c + 1];
+            if (silu) { a = silu_f(a); d = silu_f(d); }
+            o[t] = pack_bf16x2(a, d);
+        }
+        *reinterpret_cast<uint4*>(y + ((long long)b * HW + p) * ldy + cv * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ZeroSFT tail (SUPIR_v0.py:110-113): out = lerp(h_raw, GN(h) * (gamma + 1) + beta, control_scale)
+//   h      : [B, HW, C]  (= cat(h_ori, skip + zero_conv(c)))        gb : [B, HW, 2C] = (gamma | beta) conv outputs
+//   h_raw first C1 channels equal h's; the remaining C - C1 come from `skip_raw` [B, HW, C - C1]
+// ---------------------------------------------------------------------------------------------
+__global__ void sft_apply_kernel(const __nv_bfloat16* __restrict__ h, long long ldh,
+                                 const __nv_bfloat16* __restrict__ skip_raw, long long lds, int C1,
+                                 const __nv_bfloat16* __restrict__ gb, long long ldgb, __nv_bfloat16* __restrict__ out,
+                                 long long ldo, int HW, int C, int G, const double* __restrict__ sums, double count,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                 const float* __restrict__ control_scale, int pixels_per_block) {
+    extern __shared__ float sm[];
+    const int b = blockIdx.y;
+    const int cpg = C / G;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        const double dm = sums[((long long)b * G + g) * 2] / count;
+        double dv = sums[((long long)b * G + g) * 2 + 1] / count - dm * dm;
+        if (dv < 0) dv = 0;
+        const float rstd = rsqrtf((float)dv + eps);
+        const float sc = rstd * gamma[c];
+        sm[c] = sc;
+        sm[C + c] = beta[c] - (float)dm * sc;
+    }
+    __syncthreads();
+    const float cs = *control_scale;
+    const int cv_count = C >> 3;
+    const int p0 = blockIdx.x * pixels_per_block;
+    const int p1 = min(p0 + pixels_per_block, HW);
+    const long long total = (long long)(p1 - p0) * cv_count;
+    for (long long i = threadIdx.x; i < total; i += blockDim.x) {
+        const int p = p0 + (int)(i / cv_count);
+        const int cv = (int)(i % cv_count);
+        const long long row = (long long)b * HW + p;
+        const int c0 = cv * 8;
+        const uint4 uh = __ldg(reinterpret_cast<const uint4*>(h + row * ldh + c0));
+        const uint4 ug = __ldg(reinterpret_cast<const uint4*>(gb + row * ldgb + c0));
+        const uint4 ub = __ldg(reinterpret_cast<const uint4*>(gb + row * ldgb + C + c0));
+        uint4 ur = uh;
+        if (c0 >= C1) ur = __ldg(reinterpret_cast<const uint4*>(skip_raw + row * lds + (c0 - C1)));
+        const uint32_t wh[4] = {uh.x, uh.y, uh.z, uh.w}, wg[4] = {ug.x, ug.y, ug.z, ug.w},
+                       wb[4] = {ub.x, ub.y, ub.z, ub.w}, wr[4] = {ur.x, ur.y, ur.z, ur.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float2 fh = unpack_bf16x2(wh[t]), fg = unpack_bf16x2(wg[t]), fb = unpack_bf16x2(wb[t]),
+                         fr = unpack_bf16x2(wr[t]);
+            const int c = c0 + 2 * t;
+            // normalised (fp32) * (gamma + 1) + beta, each intermediate rounded like the reference's bf16 tensors
+            const float n0 = fh.x * sm[c] + sm[C + c], n1 = fh.y * sm[c + 1] + sm[C + c + 1];
+            const float a = n0 * (bf16_round(fg.x + 1.f)) + fb.x;
+            const float d = n1 * (bf16_round(fg.y + 1.f)) + fb.y;
+            o[t] = pack_bf16x2(a * cs + fr.x * (1.f - cs), d * cs + fr.y * (1.f - cs));
+        }
+        *reinterpret_cast<uint4*>(out + row * ldo + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm over the last dim (C <= 2048, C % 8 == 0): one warp per row, row kept in registers.
+// ---------------------------------------------------------------------------------------------
+template <int MAXV>  // max 16-byte vectors per lane
+__global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y,
+                                 long long ldy, long long rows, int C, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float eps) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int nv = C >> 3;
+    float v[MAXV][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < nv) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + row * ldx + vi * 8));
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float2 f = unpack_bf16x2(w[t]);
+                v[i][2 * t] = f.x; v[i][2 * t + 1] = f.y;
+                s += f.x + f.y;
+            }
+        }
+    }
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < nv) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; q += d * d; }
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / C + eps);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < nv) {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
+            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                o[t] = pack_bf16x2((v[i][2 * t] - mean) * rstd * gg[2 * t] + bb[2 * t],
+                                   (v[i][2 * t + 1] - mean) * rstd * gg[2 * t + 1] + bb[2 * t + 1]);
+            *reinterpret_cast<uint4*>(y + row * ldy + vi * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
+// row softmax for the materialised single-head VAE attention: P = softmax(S * scale), fp32 in, bf16 out
+__global__ void softmax_rows_kernel(const float* __restrict__ S, long long lds, __nv_bfloat16* __restrict__ P,
+                                    long long ldp, int cols, float scale) {
+    const long long row = blockIdx.x;
+    const float* s = S + row * lds;
+    __shared__ float red[32];
+    float m = -INFINITY;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) m = fmaxf(m, s[c]);
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -INFINITY;
+        t = warp_max(t);
+        if (threadIdx.x == 0) red[0] = t;
+    }
+    __syncthreads();
+    m = red[0];
+    __syncthreads();
+    float sum = 0.f;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) sum += __expf((s[c] - m) * scale);
+    sum = warp_sum(sum);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) red[0] = t;
+    }
+    __syncthreads();
+    const float inv = 1.f / red[0];
+    __nv_bfloat16* p = P + row * ldp;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) p[c] = __float2bfloat16_rn(__expf((s[c] - m) * scale) * inv);
+}
+
+static int gn_launch_shape(int HW, int C, int& threads, int& ppb, int& blocks_x) {
+    const int cv = C >> 3;
+    int kp = 512 / cv;
+    if (kp < 1) kp = 1;
+    threads = kp * cv;
+    // enough blocks to cover the machine a few times, but at least 32 pixels per thread-row to amortise the reduction
+    ppb = kp * 16;
+    if (ppb < 64) ppb = 64;
+    blocks_x = (HW + ppb - 1) / ppb;
+    return 0;
+}
+
+}  // namespace supir
+
+using namespace supir;
+
+extern "C" int supir_groupnorm_stats(const void* x, long long ldx, int B, int HW, int C, int groups, double* sums,
+                                     void* stream) {
+    SUPIR_REQUIRE(x && sums, "supir_groupnorm_stats: null pointer");
+    SUPIR_REQUIRE(C % 8 == 0 && C % groups == 0 && ldx % 8 == 0 && C <= 8192, "supir_groupnorm_stats: bad C=%d", C);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    SUPIR_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * B * groups, st));
+    int threads, ppb, bx;
+    gn_launch_shape(HW, C, threads, ppb, bx);
+    gn_stats_kernel<<<dim3(bx, B), threads, 2 * C * sizeof(float), st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), ldx, HW, C, groups, ppb, sums);
+    count_launch();
+    SUPIR_CHECK_CUDA(cudaGetLastError());
+    return SUPIR_OK;
+}
+
+extern "C" int supir_groupnorm_finalize(const double* sums, int n, double count, float* mean, float* var, void* stream) {
+    SUPIR_REQUIRE(sums && mean && var && n > 0, "supir_groupnorm_finalize: bad args");
+    gn_finalize_kernel<<<(n + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(sums, n, count, mean, var);
+    count_launch();
+    SUPIR_CHECK_CUDA(cudaGetLastError());
+    return SUPIR_OK;
+}
+
+extern "C" int supir_groupnorm_merge_tiles(const float* tile_mean, const float* tile_var, const float* weights, int T,
+                                           int n, float* mean, float* var, void* stream) {
+    SUPIR_REQUIRE(tile_mean && tile_var && weights && mean && var && T > 0 && n > 0, "supir_groupnorm_merge_tiles: bad args");
+    gn_merge_tiles_kernel<<<(n + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(tile_mean, tile_var,
+                                                                                              weights, T, n, mean, var);
+    count_launch();
+    SUPIR_CHECK_CUDA(cudaGetLastError());
+    return SUPIR_OK;
+}
+
+extern "C" int supir_groupnorm_apply(const void* x, long long ldx, void* y, long long ldy, int B, int HW, int C,
+                                     int groups, const double* sums, const float* mean, const float* var,
+                                     const float* gamma, const float* beta, float eps, int silu, void* stream) {
+    SUPIR_REQUIRE(x && y && (sums || (mean && var)), "supir_groupnorm_apply: null pointer");
+    SUPIR_REQUIRE(C % 8 == 0 && C % groups == 0 && ldx % 8 == 0 && ldy % 8 == 0 && C <= 8192,
+                  "supir_groupnorm_apply: bad C=%d", C);
+    int threads = 256;
+    int ppb = 16384 / C;  // ~32 KB of bf16 per block
+    if (ppb < 4) ppb = 4;
+    const int bx = (HW + ppb - 1) / ppb;
+    gn_apply_kernel<<<dim3(bx, B), threads, 2 * C * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<__nv_bfloat16*>(y), ldy, HW, C, groups, mean,
+        var, sums, (double)HW * (C / groups), gamma, beta, eps, silu, ppb);
+    count_launch();
+    SUPIR_CHECK_CUDA(cudaGetLastError());
+    return SUPIR_OK;
+}
+
+extern "C" int supir_zerosft_apply(const void* h, long long ldh, const void* skip_raw, long long lds, int C1,
+                                   const void* gamma_beta, long long ldgb, void* out, long long ldo, int B, int HW,
+                                   int C, int groups, const double* sums, const float* gn_weight, const float* gn_bias,
+                                   float eps, const float* control_scale, void* stream) {
+    SUPIR_REQUIRE(h && gamma_beta && out && sums && gn_weight && gn_bias && control_scale, "supir_zerosft_apply: null pointer");
+    SUPIR_REQUIRE(C % 8 == 0 && C1 % 8 == 0 && C % groups == 0 && (C1 == C || skip_raw), "supir_zerosft_apply: bad channels");
+    int ppb = 8192 / C;
+    if (ppb < 4) ppb = 4;
+    const int bx = (HW + ppb - 1) / ppb;
+    sft_apply_kernel<<<dim3(bx, B), 256, 2 * C * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(h), ldh, reinterpret_cast<const __nv_bfloat16*>(skip_raw), lds, C1,
+        reinterpret_cast<const __nv_bfloat16*>(gamma_beta), ldgb, reinterpret_cast<__nv_bfloat16*>(out), ldo, HW, C,
+        groups, sums, (double)HW * (C / groups), gn_weight, gn_bias, eps, control_scale, ppb);
+    count_launch();
+    SUPIR_CHECK_CUDA(cudaGetLastError());
+    return SUPIR_OK;
+}
+
+extern "C" int supir_layernorm_bf16(const void* x, long long ldx, void* y, long long ldy, long long rows, int C,
+                                    const float* gamma, const float* beta, float eps, void* stream) {
+    SUPIR_REQUIRE(x && y && gamma && beta, "supir_layernorm_bf16: null pointer");
+    SUPIR_REQUIRE(C % 8 == 0 && C <= 2048 && ldx % 8 == 0 && ldy % 8 == 0, "supir_layernorm_bf16: unsupported C=%d", C);
+    const int warps = 8;
+    const long long blocks = (rows + warps - 1) / warps;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+    __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
+    const int nv = C >> 3;
+    if (nv <= 96)
+        layernorm_kernel<3><<<(unsigned)blocks, warps * 32, 0, st>>>(xp, ldx, yp, ldy, rows, C, gamma, beta, eps);
+    else if (nv <= 160)
+        layernorm_kernel<5><<<(unsigned)blocks, warps * 32, 0, st>>>(xp, ldx, yp, ldy, rows, C, gamma, beta, eps);
+    else
+        layernorm_kernel<8><<<(unsigned)blocks, warps * 32, 0, st>>>(xp, ldx, yp, ldy, rows, C, gamma, beta, eps);
+    count_launch();
+    SUPIR_CHECK_CUDA(cudaGetLastError());
+    return SUPIR_OK;
+}
+
+extern "C" int supir_softmax_rows(const float* S, long long lds, void* P, long long ldp, long long rows, int cols,
+                                  float scale, void* stream) {
+    SUPIR_REQUIRE(S && P && rows > 0 && cols > 0, "supir_softmax_rows: bad args");
+    softmax_rows_kernel<<<(unsigned)rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        S, lds, reinterpret_cast<__nv_bfloat16*>(P), ldp, cols, scale);
+    count_launch();
+    SUPIR_CHECK_CUDA(cudaGetLastError());
+    return SUPIR_OK;
+}
