@@ -58,6 +58,107 @@ int supir_set_gemm_tile_n(int bn);
 /* debugging: override the UMMA shared-memory descriptor template / instruction descriptor (-1 = built-in default) */
 int supir_debug_set_umma_descriptors(long long smem_desc_template, long long idesc);
 
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* network entry / exit convolutions with < 8 channels on one side (smallconv.cu)                                     */
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* 3x3 pad-1 conv, Cin <= 8: x fp32, addressed x[b*sb + c*sc + y*sy + x] (a strided NCHW view, e.g. a tile of a larger
+ * image; the tile border is zero padded like tilevae.py's per-tile convs); w fp32 [Cout, Cin, 3, 3]; optional bf16
+ * NHWC residual added to the result ("h += guided_hint", SUPIR_v0.py:531); out NHWC bf16 [B, H, W, ldo].
+ * Replaces conv_in / input_hint_block (openaimodel.py:704, SUPIR_v0.py:325,482) and VAE conv_in (model.py:512-514,646-648). */
+int supir_conv3x3_small_cin(const float* x, long long sb, long long sc, long long sy, const float* w, const float* bias,
+                            const void* residual, long long ldr, void* out, long long ldo, int B, int H, int W, int Cin,
+                            int Cout, void* stream);
+/* 3x3 pad-1 conv, Cout in {3,4,8}: x NHWC bf16 [B,H,W,ldx]; w fp32 [Cout, 3, 3, Cin]; only the crop window
+ * [crop_y0, crop_y0+crop_h) x [crop_x0, crop_x0+crop_w) of the tile is computed and written to
+ * out[b*ob + c*oc + (y-crop_y0)*oy + (x-crop_x0)] (fp32, values rounded to bf16 as under autocast).
+ * Replaces UNet `out` conv (openaimodel.py:947-953), VAE conv_out (model.py:563-569,694-696) and, for tiles,
+ * crop_valid_region + the paste into the result canvas (tilevae.py:556-567, 946). */
+int supir_conv3x3_small_cout(const void* x, long long ldx, const float* w, const float* bias, float* out, long long ob,
+                             long long oc, long long oy, int B, int H, int W, int Cin, int Cout, int crop_y0, int crop_x0,
+                             int crop_h, int crop_w, void* stream);
+/* 1x1 conv on contiguous fp32 NCHW with Cin, Cout <= 8; input pre-multiplied by in_scale (decode: 1/scale_factor).
+ * Replaces quant_conv / post_quant_conv (sgm/models/autoencoder.py:297-298, 304-316). */
+int supir_conv1x1_small_nchw(const float* x, const float* w, const float* bias, float* y, int B, int Cin, int Cout,
+                             long long HW, float in_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* K1/K5/K13: GroupNorm(32 groups) [+SiLU], ZeroSFT tail, LayerNorm, row softmax (norm.cu)                            */
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* sums[B, groups, 2] (fp64) <- per-(image, group) sum and sum of squares of x [B, HW, ldx>=C] bf16. Zeroes sums first. */
+int supir_groupnorm_stats(const void* x, long long ldx, int B, int HW, int C, int groups, double* sums, void* stream);
+/* sums -> mean, biased variance (fp32), count = HW * C / groups  (tilevae.py:511-521 get_var_mean) */
+int supir_groupnorm_finalize(const double* sums, int n, double count, float* mean, float* var, void* stream);
+/* tiled VAE: mean = sum_t w_t mean_t, var = sum_t w_t var_t with w = pixels/max/sum (tilevae.py:629-648) */
+int supir_groupnorm_merge_tiles(const float* tile_mean, const float* tile_var, const float* weights, int T, int n,
+                                float* mean, float* var, void* stream);
+/* y = (x - mean) * rsqrt(var + eps) * gamma + beta, optionally followed by SiLU; statistics either from `sums`
+ * (fp64, as written by supir_groupnorm_stats) or from explicit mean/var. GroupNorm32 eps 1e-5 (util.py:258-276),
+ * Normalize eps 1e-6 (attention.py:122-125, model.py:49-52); custom_group_norm for tiles (tilevae.py:524-553). */
+int supir_groupnorm_apply(const void* x, long long ldx, void* y, long long ldy, int B, int HW, int C, int groups,
+                          const double* sums, const float* mean, const float* var, const float* gamma, const float* beta,
+                          float eps, int silu, void* stream);
+/* ZeroSFT tail (SUPIR_v0.py:110-113): out = lerp(h_raw, GN(h) * (gamma + 1) + beta, *control_scale).
+ * h [B,HW,C] is cat(h_ori, skip + zero_conv(c)); h_raw equals h on the first C1 channels and `skip_raw` on the rest;
+ * gamma_beta [B,HW,2C] holds the zero_mul | zero_add conv outputs; control_scale is a device scalar. */
+int supir_zerosft_apply(const void* h, long long ldh, const void* skip_raw, long long lds, int C1, const void* gamma_beta,
+                        long long ldgb, void* out, long long ldo, int B, int HW, int C, int groups, const double* sums,
+                        const float* gn_weight, const float* gn_bias, float eps, const float* control_scale, void* stream);
+/* nn.LayerNorm over the last dim (attention.py:437-439), eps 1e-5; C % 8 == 0, C <= 2048 */
+int supir_layernorm_bf16(const void* x, long long ldx, void* y, long long ldy, long long rows, int C, const float* gamma,
+                         const float* beta, float eps, void* stream);
+/* P = softmax(S * scale) row-wise, fp32 -> bf16 (single-head 512-dim VAE attention, model.py:187-189) */
+int supir_softmax_rows(const float* S, long long lds, void* P, long long ldp, long long rows, int cols, float scale,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* K6: attention, head_dim 64 (attention.cu)                                                                          */
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* out[b, i, h*64:(h+1)*64] = softmax(q_h k_h^T * scale) v_h ; q [B*Lq, ldq], k/v [B*Lk, ldk/ldv], head h at column h*64.
+ * Replaces F.scaled_dot_product_attention / xformers in CrossAttention (attention.py:273-277, 357-359) and
+ * ZeroCrossAttn (SUPIR_v0.py:146). */
+int supir_attention_bf16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                         void* out, long long ldo, int B, int H, int Lq, int Lk, int head_dim, float scale, void* stream);
+int supir_debug_set_attention_descriptors(long long smem_desc_template, long long idesc_pv);
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* K7/K8/K10/K12/K14 and data movement (elementwise.cu)                                                               */
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* nearest 2x upsample on NHWC bf16 (openaimodel.py:131-151, model.py:64-68) */
+int supir_upsample_nearest2x(const void* x, long long ldx, void* y, long long ldy, int B, int H, int W, int C, void* stream);
+/* im2col for 3x3 stride-2 convs: out [B*Ho*Wo, 9*C]; pad_lo = 1 (UNet Downsample, openaimodel.py:196-210) or
+ * 0 (VAE Downsample pads right/bottom only, model.py:81-85) */
+int supir_im2col_3x3_s2(const void* x, long long ldx, void* out, int B, int H, int W, int C, int Ho, int Wo, int pad_lo,
+                        void* stream);
+int supir_copy2d_bf16(const void* src, long long lds, void* dst, long long ldd, long long rows, int cols, void* stream);
+/* out = a + y * (*scale)  (ZeroCrossAttn, SUPIR_v0.py:150) */
+int supir_axpy_bf16(const void* a, long long lda, const void* y, long long ldy, void* out, long long ldo, long long rows,
+                    int cols, const float* scale, void* stream);
+int supir_nchw_f32_to_nhwc_bf16(const float* x, void* y, long long ldy, int B, int C, int HW, void* stream);
+int supir_nhwc_bf16_to_nchw_f32(const void* x, long long ldx, float* y, int B, int C, int HW, void* stream);
+int supir_f32_to_bf16(const float* x, void* y, long long n, void* stream);
+/* timestep_embedding (sgm/modules/diffusionmodules/util.py:206-230), dim even, max_period 1e4 */
+int supir_timestep_embedding(const float* t, float* out, int B, int dim, void* stream);
+/* y = [silu]( [silu](x) @ W^T + bias ) [+ add] for B <= 16 rows (time/label embedding MLPs, per-ResBlock emb_layers:
+ * openaimodel.py:664-697, 287-293); x, y, add fp32; W bf16 [N, K] */
+int supir_linear_small_m(const float* x, int ldx, const void* W, const float* bias, float* y, int ldy, int B, int N, int K,
+                         int silu_in, int silu_out, const float* add, int ldadd, void* stream);
+/* sampler step, part 1 (sampling.py:550-556 + guiders.py:65-74 + denoiser.py:71): x_hat = x + eps*noise_mul (eps may be
+ * NULL); net_in[0:n] = net_in[n:2n] = x_hat * c_in */
+int supir_edm_pre(const float* x, const float* eps, float noise_mul, float c_in, float* x_hat, float* net_in, long long n,
+                  void* stream);
+/* sampler step, part 2 (denoiser.py:73, guiders.py:59-63, sampling.py:563-569): denoised = net*c_out + x_hat per branch,
+ * CFG mix u + s (c - u), optional restore guidance den -= (den - x_center) * restore_mul, Euler update */
+int supir_edm_post(const float* x_hat, const float* net_out, const float* x_center, float c_out, float cfg_scale,
+                   float restore_mul, float sigma_hat, float dt, float* x_next, float* denoised, long long n, void* stream);
+/* K12 (sampling.py:629-659): out = (sum_j tiles_j * w) / (sum_j w) over the windows covering each pixel, accumulated in
+ * window order with fp64 products rounded to fp32 after every add. tiles [num_windows, N, C, tile, tile] fp32;
+ * windows int32 [num_windows, 4] = (hi, hi_end, wi, wi_end); weights fp64 [tile, tile] */
+int supir_tile_blend(const float* tiles, const int* windows, int num_windows, int tile, const double* weights, float* out,
+                     int N, int C, int H, int W, void* stream);
+/* K14 (distributions.py:24-41, SUPIR_model.py:45,61): z = scale * (mean + exp(0.5*clamp(logvar)) * eps), eps NULL = mode */
+int supir_gaussian_latent(const float* moments, const float* eps, float scale, float* z, int B, int Cz, long long HW,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

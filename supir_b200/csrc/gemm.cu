@@ -477,7 +477,7 @@ extern "C" int supir_gemm_bf16(const void* A, long long lda, const void* W, long
                                int M, int N, int K, const supir_epilogue* ep, void* stream) {
     SUPIR_REQUIRE(A && W && out, "supir_gemm_bf16: null pointer");
     SUPIR_REQUIRE(M > 0 && N > 0 && K > 0, "supir_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
-    SUPIR_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "supir_gemm_bf16: K/lda/ldw must be multiples of 8");
+    SUPIR_REQUIRE(lda % 8 == 0 && ldw % 8 == 0, "supir_gemm_bf16: lda/ldw must be multiples of 8");
     SUPIR_REQUIRE(lda >= K && ldw >= K, "supir_gemm_bf16: leading dims smaller than K");
     GemmKernelParams p{};
     p.M = M; p.N = N; p.K = K;

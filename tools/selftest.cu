@@ -308,6 +308,102 @@ static void perf_conv(int B, int H, int Wd, int Cin, int Cout, int bn) {
     fflush(stdout);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// attention
+// ------------------------------------------------------------------------------------------------
+static bool test_attention(int B, int H, int Lq, int Lk, int sample_rows) {
+    Rng rng(4242 + Lq + Lk * 3 + H);
+    const int C = H * 64;
+    std::vector<float> Q((size_t)B * Lq * C), K((size_t)B * Lk * C), V((size_t)B * Lk * C);
+    for (auto& v : Q) v = bf(rng.normal(1.5f));
+    for (auto& v : K) v = bf(rng.normal(1.5f));
+    for (auto& v : V) v = bf(rng.normal());
+    auto Qb = to_bf16(Q), Kb = to_bf16(K), Vb = to_bf16(V);
+    __nv_bfloat16 *dQ = dev_copy(Qb), *dK = dev_copy(Kb), *dV = dev_copy(Vb), *dO;
+    CK(cudaMalloc(&dO, (size_t)B * Lq * C * 2 + 16));
+    CK(cudaMemset(dO, 0xFF, (size_t)B * Lq * C * 2));
+    const float scale = 0.125f;
+    int rc = supir_attention_bf16(dQ, C, dK, C, dV, C, dO, C, B, H, Lq, Lk, 64, scale, nullptr);
+    if (rc) {
+        printf("supir_attention_bf16 rc=%d: %s\n", rc, supir_last_error());
+        g_fail++;
+        return false;
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        printf("attention kernel failed: %s\n", cudaGetErrorString(e));
+        exit(3);
+    }
+    std::vector<__nv_bfloat16> out((size_t)B * Lq * C);
+    CK(cudaMemcpy(out.data(), dO, out.size() * 2, cudaMemcpyDeviceToHost));
+    double max_err = 0, max_ref = 0;
+    long long bad = 0;
+    std::mt19937 pick(17);
+    const long long rows_total = (long long)B * H * Lq;
+    const long long checks = sample_rows > 0 && sample_rows < rows_total ? sample_rows : rows_total;
+    std::vector<double> sc(Lk);
+    for (long long t = 0; t < checks; ++t) {
+        const long long idx = checks == rows_total ? t : (long long)(pick() % rows_total);
+        const int i = (int)(idx % Lq);
+        const int h = (int)((idx / Lq) % H);
+        const int b = (int)(idx / ((long long)Lq * H));
+        const float* q = &Q[((size_t)b * Lq + i) * C + h * 64];
+        double mx = -1e30;
+        for (int j = 0; j < Lk; ++j) {
+            const float* k = &K[((size_t)b * Lk + j) * C + h * 64];
+            double s = 0;
+            for (int d = 0; d < 64; ++d) s += (double)q[d] * k[d];
+            sc[j] = s * scale;
+            if (sc[j] > mx) mx = sc[j];
+        }
+        double den = 0;
+        for (int j = 0; j < Lk; ++j) { sc[j] = exp(sc[j] - mx); den += sc[j]; }
+        for (int d = 0; d < 64; ++d) {
+            double o = 0;
+            for (int j = 0; j < Lk; ++j) o += sc[j] * V[((size_t)b * Lk + j) * C + h * 64 + d];
+            const float ref = (float)(o / den);
+            const float got = __bfloat162float(out[((size_t)b * Lq + i) * C + h * 64 + d]);
+            const double err = fabs((double)got - ref);
+            if (!(err <= 0.02 + 0.02 * fabs(ref))) bad++;
+            if (err > max_err || !std::isfinite(err)) max_err = err;
+            if (fabs(ref) > max_ref) max_ref = fabs(ref);
+        }
+    }
+    char name[256];
+    snprintf(name, sizeof(name), "attention B=%d H=%d Lq=%d Lk=%d", B, H, Lq, Lk);
+    bool ok = report(name, max_err, max_ref, 0.02, bad);
+    cudaFree(dQ); cudaFree(dK); cudaFree(dV); cudaFree(dO);
+    return ok;
+}
+
+static void perf_attention(int B, int H, int Lq, int Lk) {
+    const int C = H * 64;
+    __nv_bfloat16 *dQ, *dK, *dV, *dO;
+    CK(cudaMalloc(&dQ, (size_t)B * Lq * C * 2));
+    CK(cudaMalloc(&dK, (size_t)B * Lk * C * 2));
+    CK(cudaMalloc(&dV, (size_t)B * Lk * C * 2));
+    CK(cudaMalloc(&dO, (size_t)B * Lq * C * 2));
+    CK(cudaMemset(dQ, 0x11, (size_t)B * Lq * C * 2));
+    CK(cudaMemset(dK, 0x11, (size_t)B * Lk * C * 2));
+    CK(cudaMemset(dV, 0x11, (size_t)B * Lk * C * 2));
+    for (int i = 0; i < 3; ++i) supir_attention_bf16(dQ, C, dK, C, dV, C, dO, C, B, H, Lq, Lk, 64, 0.125f, nullptr);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int iters = 10;
+    cudaEventRecord(e0);
+    for (int i = 0; i < iters; ++i) supir_attention_bf16(dQ, C, dK, C, dV, C, dO, C, B, H, Lq, Lk, 64, 0.125f, nullptr);
+    cudaEventRecord(e1);
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ms /= iters;
+    printf("[PERF] attention B=%d H=%d Lq=%d Lk=%d : %.3f ms  %.1f TFLOP/s\n", B, H, Lq, Lk, ms,
+           4.0 * B * H * (double)Lq * Lk * 64 / ms / 1e9);
+    cudaFree(dQ); cudaFree(dK); cudaFree(dV); cudaFree(dO);
+    fflush(stdout);
+}
+
 // descriptor bring-up: try the default, then a few alternates, on a tiny identity GEMM
 static void bringup() {
     printf("== bring-up: identity GEMM 128x64x64 with default descriptors\n");
@@ -363,6 +459,22 @@ int main(int argc, char** argv) {
         test_conv(2, 32, 32, 2560, 1280, 5000, false, true);
         test_conv(1, 150, 150, 128, 128, 20000, false, false);
         test_conv(2, 8, 8, 128, 256, 0, false, false);
+    }
+    if (what == "attn" || what == "all") {
+        test_attention(1, 1, 128, 128, 0);
+        test_attention(1, 2, 128, 256, 0);
+        test_attention(2, 3, 200, 77, 0);
+        test_attention(1, 2, 333, 500, 0);
+        test_attention(2, 10, 1024, 1024, 2000);
+        test_attention(2, 20, 4096, 4096, 500);
+        test_attention(2, 10, 4096, 77, 2000);
+    }
+    if (what == "attnperf" || what == "all") {
+        perf_attention(2, 10, 4096, 4096);
+        perf_attention(2, 20, 1024, 1024);
+        perf_attention(2, 10, 16384, 16384);
+        perf_attention(2, 10, 4096, 77);
+        perf_attention(2, 20, 1024, 77);
     }
     if (what == "perf" || what == "all") {
         for (int bn : {128, 256}) {
