@@ -84,8 +84,12 @@ int supir_conv1x1_small_nchw(const float* x, const float* w, const float* bias, 
 /* ------------------------------------------------------------------------------------------------------------------ */
 /* K1/K5/K13: GroupNorm(32 groups) [+SiLU], ZeroSFT tail, LayerNorm, row softmax (norm.cu)                            */
 /* ------------------------------------------------------------------------------------------------------------------ */
-/* sums[B, groups, 2] (fp64) <- per-(image, group) sum and sum of squares of x [B, HW, ldx>=C] bf16. Zeroes sums first. */
-int supir_groupnorm_stats(const void* x, long long ldx, int B, int HW, int C, int groups, double* sums, void* stream);
+/* ws[0 : B*groups*2] (fp64) <- per-(image, group) sum and sum of squares of x [B, HW, ldx>=C] bf16; the rest of the
+ * caller-provided workspace (size in doubles from supir_groupnorm_stats_workspace) holds per-block partials so that the
+ * reduction order is fixed: results are bit-reproducible run to run. Pass `ws` as `sums` to the apply functions. */
+long long supir_groupnorm_stats_workspace(int B, int HW, int C, int groups);
+int supir_groupnorm_stats(const void* x, long long ldx, int B, int HW, int C, int groups, double* ws, long long ws_doubles,
+                          void* stream);
 /* sums -> mean, biased variance (fp32), count = HW * C / groups  (tilevae.py:511-521 get_var_mean) */
 int supir_groupnorm_finalize(const double* sums, int n, double count, float* mean, float* var, void* stream);
 /* tiled VAE: mean = sum_t w_t mean_t, var = sum_t w_t var_t with w = pixels/max/sum (tilevae.py:629-648) */
@@ -150,9 +154,17 @@ int supir_edm_pre(const float* x, const float* eps, float noise_mul, float c_in,
  * CFG mix u + s (c - u), optional restore guidance den -= (den - x_center) * restore_mul, Euler update */
 int supir_edm_post(const float* x_hat, const float* net_out, const float* x_center, float c_out, float cfg_scale,
                    float restore_mul, float sigma_hat, float dt, float* x_next, float* denoised, long long n, void* stream);
+/* unfused sampler arithmetic for callers that keep the reference's denoiser/guider objects in the loop:
+ * out = a*alpha + b*beta (b may be NULL; denoiser.py:73, sampling.py:556,567-569) and the CFG pair reduction
+ * out[n] = u_n + scale[n] * (c_n - u_n) with x = [u ; c] (guiders.py:59-63, sampling_utils.py:7-9) */
+int supir_axpby_f32(const float* a, float alpha, const float* b, float beta, float* out, long long n, void* stream);
+int supir_cfg_combine(const float* x, const float* scale, float* out, int N, long long per_sample, void* stream);
 /* K12 (sampling.py:629-659): out = (sum_j tiles_j * w) / (sum_j w) over the windows covering each pixel, accumulated in
  * window order with fp64 products rounded to fp32 after every add. tiles [num_windows, N, C, tile, tile] fp32;
- * windows int32 [num_windows, 4] = (hi, hi_end, wi, wi_end); weights fp64 [tile, tile] */
+ * windows int32 [num_windows, 4] = (hi, hi_end, wi, wi_end), hi < 0 marks an unused slot; weights fp64 [tile, tile].
+ * supir_tile_gather is the matching window extraction (sampling.py:633-641): out[j] = src[:, :, window j]. */
+int supir_tile_gather(const float* src, const int* windows, int num_windows, int tile, float* out, int N, int C, int H,
+                      int W, void* stream);
 int supir_tile_blend(const float* tiles, const int* windows, int num_windows, int tile, const double* weights, float* out,
                      int N, int C, int H, int W, void* stream);
 /* K14 (distributions.py:24-41, SUPIR_model.py:45,61): z = scale * (mean + exp(0.5*clamp(logvar)) * eps), eps NULL = mode */

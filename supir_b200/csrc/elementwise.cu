@@ -203,6 +203,39 @@ __global__ void edm_post_kernel(const float* __restrict__ x_hat, const float* __
     }
 }
 
+
+// out = a * alpha + b * beta (fp32; b may be NULL) — the unfused forms of the sampler arithmetic, used when the
+// reference's own denoiser/guider objects drive the loop (denoiser.py:73, sampling.py:556, 567-569)
+__global__ void axpby_f32_kernel(const float* __restrict__ a, float alpha, const float* __restrict__ b, float beta,
+                                 float* __restrict__ out, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = a[i] * alpha + (b ? b[i] * beta : 0.f);
+}
+// LinearCFG / VanillaCFG combine (guiders.py:59-63, sampling_utils.py:7-9): out[n] = u + s_n (c - u), x = [u ; c]
+__global__ void cfg_combine_kernel(const float* __restrict__ x, const float* __restrict__ scale, float* __restrict__ out,
+                                   int N, long long per) {
+    const long long total = (long long)N * per;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const float u = x[i], c = x[total + i];
+        out[i] = u + scale[i / per] * (c - u);
+    }
+}
+
+
+// K12 gather: out[j, n, c, :, :] = src[n, c, hi_j : hi_j + tile, wi_j : wi_j + tile]  (sampling.py:633-641 slices)
+__global__ void tile_gather_kernel(const float* __restrict__ src, const int* __restrict__ win, int num_win, int tile,
+                                   float* __restrict__ out, int N, int C, int H, int W) {
+    const long long total = (long long)num_win * N * C * tile * tile;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int tx = (int)(i % tile);
+        const int ty = (int)((i / tile) % tile);
+        const int c = (int)((i / ((long long)tile * tile)) % C);
+        const int n = (int)((i / ((long long)tile * tile * C)) % N);
+        const int j = (int)(i / ((long long)tile * tile * C * N));
+        out[i] = src[(((long long)n * C + c) * H + win[4 * j] + ty) * W + win[4 * j + 2] + tx];
+    }
+}
+
 // K12: Gaussian-weighted window blend, evaluated per output pixel in the reference's window order so that the fp32
 // rounding sequence of `x_next[win] += _x * w; count[win] += w; x_next /= count` (sampling.py:656-659) is reproduced:
 // the products and sums are formed in fp64 (w is float64) and rounded to fp32 after every accumulation.
@@ -217,6 +250,7 @@ __global__ void tile_blend_kernel(const float* __restrict__ tiles, const int* __
         float acc = 0.f, cnt = 0.f;
         for (int j = 0; j < num_win; ++j) {
             const int hi = win[4 * j], he = win[4 * j + 1], wi = win[4 * j + 2], we = win[4 * j + 3];
+            if (hi < 0) continue;  // padding slot of a sharded run
             if (y < hi || y >= he || x < wi || x >= we) continue;
             const int ty = y - hi, tx = x - wi;
             const double w = weights[ty * tile + tx];
@@ -344,6 +378,28 @@ extern "C" int supir_edm_post(const float* x_hat, const float* net_out, const fl
     SUPIR_REQUIRE(x_hat && net_out && x_next && n > 0, "supir_edm_post: bad args");
     edm_post_kernel<<<blocks_for(n, 256), 256, 0, ST(stream)>>>(x_hat, net_out, x_center, c_out, cfg_scale, restore_mul,
                                                                 sigma_hat, dt, x_next, denoised, n);
+    DONE();
+}
+
+
+extern "C" int supir_axpby_f32(const float* a, float alpha, const float* b, float beta, float* out, long long n, void* stream) {
+    SUPIR_REQUIRE(a && out && n > 0, "supir_axpby_f32: bad args");
+    axpby_f32_kernel<<<blocks_for(n, 256), 256, 0, ST(stream)>>>(a, alpha, b, beta, out, n);
+    DONE();
+}
+
+extern "C" int supir_cfg_combine(const float* x, const float* scale, float* out, int N, long long per_sample, void* stream) {
+    SUPIR_REQUIRE(x && scale && out && N > 0 && per_sample > 0, "supir_cfg_combine: bad args");
+    cfg_combine_kernel<<<blocks_for((long long)N * per_sample, 256), 256, 0, ST(stream)>>>(x, scale, out, N, per_sample);
+    DONE();
+}
+
+
+extern "C" int supir_tile_gather(const float* src, const int* windows, int num_windows, int tile, float* out, int N, int C,
+                                 int H, int W, void* stream) {
+    SUPIR_REQUIRE(src && windows && out && num_windows > 0, "supir_tile_gather: bad args");
+    tile_gather_kernel<<<blocks_for((long long)num_windows * N * C * tile * tile, 256), 256, 0, ST(stream)>>>(
+        src, windows, num_windows, tile, out, N, C, H, W);
     DONE();
 }
 

@@ -11,55 +11,80 @@
 namespace supir {
 
 // ---------------------------------------------------------------------------------------------
-// GroupNorm statistics: per (image, group) sum and sum of squares, accumulated in fp64.
-// Block = KP pixels x (C/8) channel-vectors; each thread keeps 8 channel accumulators for a strided subset of the
-// block's pixel chunk, then the block reduces to groups in shared memory and issues one fp64 atomicAdd per group.
+// GroupNorm statistics: per (image, group) sum and sum of squares in fp64 — deterministic (no floating-point atomics):
+// block = KP pixels x (C/8) channel-vectors; per-thread fp32 partials over a pixel chunk -> fixed-order shared-memory
+// reduction -> per-block fp64 group partials in the workspace; the last block of an image to finish (integer ticket)
+// adds the block partials in block order into sums[b, g, 0:2].
+// workspace layout (doubles): [B*G*2 final sums][B*nblk*G*2 block partials][B tickets (as uint32 in 8-byte slots)]
 // ---------------------------------------------------------------------------------------------
 __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int HW, int C, int G,
-                                int pixels_per_block, double* __restrict__ sums) {
-    extern __shared__ float sm[];  // [2][C]
+                                int pixels_per_block, double* __restrict__ ws, int B) {
+    extern __shared__ float sm[];  // [2][kp][C]
+    __shared__ int is_last;
     const int cv_count = C >> 3;
     const int kp = blockDim.x / cv_count;
     const int cv = threadIdx.x % cv_count;
     const int pl = threadIdx.x / cv_count;
     const int b = blockIdx.y;
+    const int nblk = gridDim.x;
     const int p0 = blockIdx.x * pixels_per_block;
     const int p1 = min(p0 + pixels_per_block, HW);
+    double* sums = ws;
+    double* partial = ws + (long long)B * G * 2;
+    unsigned int* tickets = reinterpret_cast<unsigned int*>(ws + (long long)B * G * 2 + (long long)B * nblk * G * 2);
     float s[8], ss[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
-    if (pl < kp) {
-        const __nv_bfloat16* base = x + ((long long)b * HW) * ldx + cv * 8;
-        for (int p = p0 + pl; p < p1; p += kp) {
-            const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (long long)p * ldx));
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    const __nv_bfloat16* base = x + ((long long)b * HW) * ldx + cv * 8;
+    for (int p = p0 + pl; p < p1; p += kp) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (long long)p * ldx));
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const float2 f = unpack_bf16x2(w[t]);
-                s[2 * t] += f.x; ss[2 * t] += f.x * f.x;
-                s[2 * t + 1] += f.y; ss[2 * t + 1] += f.y * f.y;
-            }
+        for (int t = 0; t < 4; ++t) {
+            const float2 f = unpack_bf16x2(w[t]);
+            s[2 * t] += f.x; ss[2 * t] += f.x * f.x;
+            s[2 * t + 1] += f.y; ss[2 * t + 1] += f.y * f.y;
         }
     }
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-    __syncthreads();
-    if (pl < kp) {
+    float* sm_s = sm;
+    float* sm_q = sm + kp * C;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            atomicAdd(&sm[cv * 8 + j], s[j]);
-            atomicAdd(&sm[C + cv * 8 + j], ss[j]);
-        }
+    for (int j = 0; j < 8; ++j) {
+        sm_s[pl * C + cv * 8 + j] = s[j];
+        sm_q[pl * C + cv * 8 + j] = ss[j];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = 0.f, q = 0.f;
+        for (int r = 0; r < kp; ++r) { a += sm_s[r * C + c]; q += sm_q[r * C + c]; }
+        sm_s[c] = a;   // row 0, own column only
+        sm_q[c] = q;
     }
     __syncthreads();
     const int cpg = C / G;
     for (int g = threadIdx.x; g < G; g += blockDim.x) {
         double a = 0, q = 0;
-        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-            a += sm[c];
-            q += sm[C + c];
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) { a += sm_s[c]; q += sm_q[c]; }
+        double* dst = partial + (((long long)b * nblk + blockIdx.x) * G + g) * 2;
+        dst[0] = a;
+        dst[1] = q;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(&tickets[2 * b], 1u) == (unsigned)(nblk - 1));
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        for (int g = threadIdx.x; g < G; g += blockDim.x) {
+            double a = 0, q = 0;
+            for (int k = 0; k < nblk; ++k) {
+                const double* src = partial + (((long long)b * nblk + k) * G + g) * 2;
+                a += __ldcg(src);
+                q += __ldcg(src + 1);
+            }
+            sums[((long long)b * G + g) * 2] = a;
+            sums[((long long)b * G + g) * 2 + 1] = q;
         }
-        atomicAdd(&sums[((long long)b * G + g) * 2], a);
-        atomicAdd(&sums[((long long)b * G + g) * 2 + 1], q);
     }
 }
 
@@ -306,16 +331,31 @@ static int gn_launch_shape(int HW, int C, int& threads, int& ppb, int& blocks_x)
 
 using namespace supir;
 
-extern "C" int supir_groupnorm_stats(const void* x, long long ldx, int B, int HW, int C, int groups, double* sums,
-                                     void* stream) {
-    SUPIR_REQUIRE(x && sums, "supir_groupnorm_stats: null pointer");
-    SUPIR_REQUIRE(C % 8 == 0 && C % groups == 0 && ldx % 8 == 0 && C <= 8192, "supir_groupnorm_stats: bad C=%d", C);
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    SUPIR_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * B * groups, st));
+extern "C" long long supir_groupnorm_stats_workspace(int B, int HW, int C, int groups) {
+    if (C % 8 != 0 || C <= 0) return -1;
     int threads, ppb, bx;
     gn_launch_shape(HW, C, threads, ppb, bx);
-    gn_stats_kernel<<<dim3(bx, B), threads, 2 * C * sizeof(float), st>>>(
-        reinterpret_cast<const __nv_bfloat16*>(x), ldx, HW, C, groups, ppb, sums);
+    return (long long)B * groups * 2 + (long long)B * bx * groups * 2 + B;
+}
+
+extern "C" int supir_groupnorm_stats(const void* x, long long ldx, int B, int HW, int C, int groups, double* ws,
+                                     long long ws_doubles, void* stream) {
+    SUPIR_REQUIRE(x && ws, "supir_groupnorm_stats: null pointer");
+    SUPIR_REQUIRE(C % 8 == 0 && C % groups == 0 && ldx % 8 == 0 && C <= 8192, "supir_groupnorm_stats: bad C=%d", C);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int threads, ppb, bx;
+    gn_launch_shape(HW, C, threads, ppb, bx);
+    const long long need = (long long)B * groups * 2 + (long long)B * bx * groups * 2 + B;
+    SUPIR_REQUIRE(ws_doubles >= need, "supir_groupnorm_stats: workspace of %lld doubles < %lld required", ws_doubles, need);
+    SUPIR_CHECK_CUDA(cudaMemsetAsync(ws + need - B, 0, sizeof(double) * B, st));   // tickets
+    const int kp = threads / (C >> 3);
+    const size_t smem = (size_t)2 * kp * C * sizeof(float);
+    static size_t max_set = 0;
+    if (smem > 48 * 1024 && smem > max_set) {
+        SUPIR_CHECK_CUDA(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        max_set = smem;
+    }
+    gn_stats_kernel<<<dim3(bx, B), threads, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, HW, C, groups, ppb, ws, B);
     count_launch();
     SUPIR_CHECK_CUDA(cudaGetLastError());
     return SUPIR_OK;

@@ -1,0 +1,136 @@
+"""SUPIRModel engine on the B200 backend (reference: SUPIR/models/SUPIR_model.py:12-179 on top of
+sgm/models/diffusion.py:22-83).
+
+The reference keeps this layer as Python orchestration (stage-1 encode/decode, conditioning, sampler call, decode); it is
+the CALLER of the hot path. This class offers the same constructor keys (so `options/SUPIR_v0*.yaml` instantiates it
+through supir_b200.config) and the same methods, wired to this package's networks, samplers and VAE. The text conditioner
+(CLIP encoders) is outside the hot path: pass `conditioner_config=None` and hand `c` / `uc`
+dictionaries to `batchify_sample`, or install the reference's `sgm` package for it.
+"""
+import copy
+import random
+
+import torch
+import torch.nn as nn
+
+from .config import get_obj_from_str, instantiate_from_config
+from .sampling import FusedDenoiser
+from .vae import DiagonalGaussianDistribution, VAEHook
+
+
+def _get(cfg, key, default=None):
+    return cfg.get(key, default) if hasattr(cfg, "get") else getattr(cfg, key, default)
+
+
+class SUPIRModel(nn.Module):
+    def __init__(self, control_stage_config, network_config, denoiser_config, first_stage_config, conditioner_config=None,
+                 sampler_config=None, network_wrapper=None, ae_dtype="fp32", diffusion_dtype="fp32", scale_factor=1.0,
+                 p_p="", n_p="", disable_first_stage_autocast=False, **unused):
+        super().__init__()
+        wrapper_cls = get_obj_from_str(network_wrapper or "sgm.modules.diffusionmodules.wrappers.ControlWrapper")
+        self.model = wrapper_cls(instantiate_from_config(network_config))
+        self.model.load_control_model(instantiate_from_config(control_stage_config))
+        self.denoiser = instantiate_from_config(denoiser_config)
+        self.sampler_config = copy.deepcopy(sampler_config)
+        self.sampler = instantiate_from_config(sampler_config) if sampler_config is not None else None
+        self.conditioner = None
+        if conditioner_config is not None:
+            try:
+                self.conditioner = instantiate_from_config(conditioner_config)
+            except (ImportError, ModuleNotFoundError, AttributeError) as e:  # text encoders live outside this package
+                self._conditioner_error = e
+        self.first_stage_model = instantiate_from_config(first_stage_config).eval()
+        for p in self.first_stage_model.parameters():
+            p.requires_grad = False
+        self.first_stage_model.denoise_encoder = copy.deepcopy(self.first_stage_model.encoder)
+        self.scale_factor = scale_factor
+        assert ae_dtype in ("fp32", "fp16", "bf16") and diffusion_dtype in ("fp32", "fp16", "bf16")
+        if ae_dtype == "fp16":
+            raise RuntimeError("fp16 cause NaN in AE")
+        self.ae_dtype = {"fp32": torch.float32, "bf16": torch.bfloat16}[ae_dtype]
+        self.model.dtype = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}[diffusion_dtype]
+        self.p_p, self.n_p = p_p, n_p
+
+    # ---- first stage (SUPIR_model.py:41-69) ----
+    @torch.no_grad()
+    def encode_first_stage(self, x):
+        return self.scale_factor * self.first_stage_model.encode(x)
+
+    @torch.no_grad()
+    def encode_first_stage_with_denoise(self, x, use_sample=True, is_stage1=False):
+        enc = self.first_stage_model.denoise_encoder_s1 if is_stage1 else self.first_stage_model.denoise_encoder
+        posterior = DiagonalGaussianDistribution(self.first_stage_model.quant_conv(enc(x)))
+        z = posterior.sample() if use_sample else posterior.mode()
+        return self.scale_factor * z
+
+    @torch.no_grad()
+    def decode_first_stage(self, z):
+        return self.first_stage_model.decode(1.0 / self.scale_factor * z).float()
+
+    @torch.no_grad()
+    def batchify_denoise(self, x, is_stage1=False):
+        return self.decode_first_stage(self.encode_first_stage_with_denoise(x, use_sample=False, is_stage1=is_stage1))
+
+    def init_tile_vae(self, encoder_tile_size=512, decoder_tile_size=64):
+        """SUPIR_model.py:138-150."""
+        fs = self.first_stage_model
+        for net, size, dec in ((fs.denoise_encoder, encoder_tile_size, False), (fs.encoder, encoder_tile_size, False),
+                               (fs.decoder, decoder_tile_size, True)):
+            net.forward = VAEHook(net, size, is_decoder=dec, fast_decoder=False, fast_encoder=False, color_fix=False, to_gpu=True)
+
+    # ---- sampling (SUPIR_model.py:79-136) ----
+    def make_sampler(self, num_steps, restoration_scale, s_churn, s_noise, cfg_scale, use_linear_CFG, cfg_scale_start):
+        cfg = copy.deepcopy(self.sampler_config)
+        params = cfg["params"]
+        params["num_steps"] = num_steps
+        g = params["guider_config"]["params"]
+        g["scale_min"] = cfg_scale
+        g["scale"] = cfg_scale_start if use_linear_CFG else cfg_scale
+        params["restore_cfg"], params["s_churn"], params["s_noise"] = restoration_scale, s_churn, s_noise
+        return instantiate_from_config(cfg)
+
+    def prepare_condition(self, _z, p, p_p, n_p, N):
+        if self.conditioner is None:
+            raise RuntimeError("no text conditioner is attached (it is outside the accelerated hot path): "
+                               "pass c= and uc= to batchify_sample, or install the reference's sgm package")
+        batch = {"original_size_as_tuple": torch.tensor([1024, 1024]).repeat(N, 1).to(_z.device),
+                 "crop_coords_top_left": torch.tensor([0, 0]).repeat(N, 1).to(_z.device),
+                 "target_size_as_tuple": torch.tensor([1024, 1024]).repeat(N, 1).to(_z.device),
+                 "aesthetic_score": torch.tensor([9.0]).repeat(N, 1).to(_z.device), "control": _z}
+        batch_uc = copy.deepcopy(batch)
+        batch_uc["txt"] = [n_p for _ in p]
+        batch["txt"] = ["".join([_p, p_p]) for _p in p]
+        return self.conditioner.get_unconditional_conditioning(batch, batch_uc)
+
+    @torch.no_grad()
+    def batchify_sample(self, x, p=None, p_p="default", n_p="default", num_steps=100, restoration_scale=4.0, s_churn=0,
+                        s_noise=1.003, cfg_scale=4.0, seed=-1, num_samples=1, control_scale=1, color_fix_type="None",
+                        use_linear_CFG=False, use_linear_control_scale=False, cfg_scale_start=1.0, control_scale_start=0.0,
+                        c=None, uc=None, **kwargs):
+        """x: [N, 3, H, W] in [-1, 1]. `c` / `uc` (dicts with 'crossattn' [N,77,2048] and 'vector' [N,2816]) replace the
+        text conditioner when given; 'control' is filled in here like prepare_condition does."""
+        assert color_fix_type in ["Wavelet", "AdaIn", "None"]
+        if color_fix_type != "None":
+            raise NotImplementedError("colour fix is post-processing outside the accelerated hot path (SURVEY.md §8f)")
+        N = len(x)
+        if num_samples > 1:
+            assert N == 1
+            N = num_samples
+            x = x.repeat(N, 1, 1, 1)
+        self.sampler = self.make_sampler(num_steps, restoration_scale, s_churn, s_noise, cfg_scale, use_linear_CFG, cfg_scale_start)
+        if seed == -1:
+            seed = random.randint(0, 65535)
+        random.seed(seed)
+        torch.manual_seed(seed)
+        _z = self.encode_first_stage_with_denoise(x, use_sample=False)
+        x_stage1 = self.decode_first_stage(_z)
+        z_stage1 = self.encode_first_stage(x_stage1)
+        if c is None:
+            c, uc = self.prepare_condition(_z, p, self.p_p if p_p == "default" else p_p, self.n_p if n_p == "default" else n_p, N)
+        else:
+            c, uc = dict(c, control=_z), dict(uc, control=_z)
+        denoiser = FusedDenoiser(self.denoiser, self.model)
+        noised_z = torch.randn_like(_z).to(_z.device)
+        _samples = self.sampler(denoiser, noised_z, cond=c, uc=uc, x_center=z_stage1, control_scale=control_scale,
+                                use_linear_control_scale=use_linear_control_scale, control_scale_start=control_scale_start)
+        return self.decode_first_stage(_samples)

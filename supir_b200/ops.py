@@ -1,0 +1,317 @@
+"""Thin PyTorch-tensor front end of the C ABI: pointer/stride extraction, output allocation, argument checks.
+
+PyTorch owns every buffer (weights, activations, RNG); kernels run on torch's current CUDA stream so that calls can be
+captured into CUDA graphs. Channels-last activations are 2-D bf16 tensors [B*H*W, C] whose row stride is the leading
+dimension handed to the kernels (column slices of wider buffers are fine).
+"""
+import ctypes
+
+import torch
+
+from . import _native
+from ._native import Epilogue, call
+
+BF16 = torch.bfloat16
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _native.SupirNativeError("supir_b200 kernels need CUDA tensors (there is no CPU fallback)")
+
+
+def _mat(t, dtype=BF16):
+    assert t.dim() == 2 and t.stride(1) == 1 and t.dtype == dtype, (t.shape, t.stride(), t.dtype)
+    return t
+
+
+class Pool:
+    """Free-list of scratch tensors keyed by (dtype, numel). Inside CUDA-graph capture the tensors come from the graph's
+    private pool and stay valid for the graph's lifetime; reuse keeps the footprint bounded."""
+
+    def __init__(self):
+        self.free = {}
+        self.all = []
+
+    def get(self, shape, dtype=BF16, device=None):
+        n = 1
+        for s in shape:
+            n *= int(s)
+        key = (dtype, n)
+        lst = self.free.get(key)
+        if lst:
+            return lst.pop().view(*shape)
+        t = torch.empty(n, dtype=dtype, device=device or "cuda")
+        self.all.append(t)
+        return t.view(*shape)
+
+    def put(self, *ts):
+        for t in ts:
+            if t is None:
+                continue
+            base = t if t._base is None else t._base
+            self.free.setdefault((base.dtype, base.numel()), []).append(base.view(-1))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# tensor-core ops
+# ------------------------------------------------------------------------------------------------------------------
+def _epilogue(bias, rowvec, rows_per_batch, residual, act, out_f32):
+    ep = Epilogue()
+    ep.bias = None if bias is None else bias.data_ptr()
+    ep.rowvec = None if rowvec is None else rowvec.data_ptr()
+    ep.rows_per_batch = int(rows_per_batch)
+    ep.rowvec_ld = 0 if rowvec is None else int(rowvec.stride(0))
+    ep.residual = None if residual is None else residual.data_ptr()
+    ep.ldr = 0 if residual is None else int(residual.stride(0))
+    ep.act = int(act)
+    ep.out_f32 = int(out_f32)
+    return ep
+
+
+def gemm(a, w, out, bias=None, rowvec=None, rows_per_batch=0, residual=None, act=0):
+    """out[M, N'] = epilogue(a[M, K] @ w[N, K]^T); N' = N/2 for act=2 (GEGLU). `out` may be fp32 or bf16."""
+    _need_cuda(a, w, out)
+    _mat(a), _mat(w)
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and out.shape[0] == M and out.shape[1] == (N // 2 if act == 2 else N), (a.shape, w.shape, out.shape)
+    ep = _epilogue(bias, rowvec, rows_per_batch, residual, act, out.dtype == torch.float32)
+    call("supir_gemm_bf16", _ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(out), out.stride(0), M, N, K,
+         ctypes.byref(ep), _stream())
+    return out
+
+
+def conv3x3(x, B, H, W, wp, out, bias=None, rowvec=None, residual=None, act=0):
+    """3x3/s1/p1 conv on NHWC: x [B*H*W, Cin] (row stride = ld), wp [Cout, 9*Cin] packed (kh, kw, cin)."""
+    _need_cuda(x, wp, out)
+    _mat(x), _mat(wp)
+    Cin = x.shape[1]
+    Cout = wp.shape[0]
+    assert x.shape[0] == B * H * W and wp.shape[1] == 9 * Cin and wp.is_contiguous() and out.shape == (B * H * W, Cout)
+    ep = _epilogue(bias, rowvec, 0, residual, act, out.dtype == torch.float32)
+    call("supir_conv3x3_bf16", _ptr(x), x.stride(0), _ptr(wp), _ptr(out), out.stride(0), B, H, W, Cin, Cout,
+         ctypes.byref(ep), _stream())
+    return out
+
+
+def attention(q, k, v, out, B, heads, Lq, Lk, scale=None):
+    _need_cuda(q, k, v, out)
+    for t in (q, k, v, out):
+        _mat(t)
+    d = q.shape[1] // heads
+    call("supir_attention_bf16", _ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out),
+         out.stride(0), B, heads, Lq, Lk, d, float(scale if scale is not None else d ** -0.5), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# normalisation
+# ------------------------------------------------------------------------------------------------------------------
+def groupnorm_ws_size(B, HW, C, groups=32):
+    """doubles needed by groupnorm_stats (final sums first, then per-block partials and tickets)."""
+    n = int(_native.load().supir_groupnorm_stats_workspace(B, HW, C, groups))
+    if n < 0:
+        raise _native.SupirNativeError(f"groupnorm: unsupported channel count {C}")
+    return n
+
+
+def groupnorm_stats(x, B, HW, ws, groups=32):
+    """ws: float64 workspace of groupnorm_ws_size() elements; ws[:B*groups*2] receives (sum, sumsq) per (image, group)."""
+    _need_cuda(x, ws)
+    _mat(x)
+    assert ws.dtype == torch.float64
+    call("supir_groupnorm_stats", _ptr(x), x.stride(0), B, HW, x.shape[1], groups, _ptr(ws), ws.numel(), _stream())
+    return ws
+
+
+def groupnorm_finalize(sums, n, count, mean, var):
+    call("supir_groupnorm_finalize", _ptr(sums), n, float(count), _ptr(mean), _ptr(var), _stream())
+
+
+def groupnorm_merge_tiles(tile_mean, tile_var, weights, mean, var):
+    T, n = tile_mean.shape
+    call("supir_groupnorm_merge_tiles", _ptr(tile_mean), _ptr(tile_var), _ptr(weights), T, n, _ptr(mean), _ptr(var), _stream())
+
+
+def groupnorm_apply(x, B, HW, out, gamma, beta, eps, silu, sums=None, mean=None, var=None, groups=32):
+    _need_cuda(x, out)
+    _mat(x), _mat(out)
+    call("supir_groupnorm_apply", _ptr(x), x.stride(0), _ptr(out), out.stride(0), B, HW, x.shape[1], groups, _ptr(sums),
+         _ptr(mean), _ptr(var), _ptr(gamma), _ptr(beta), float(eps), int(silu), _stream())
+    return out
+
+
+def zerosft_apply(h, skip_raw, C1, gamma_beta, out, B, HW, sums, gn_w, gn_b, eps, control_scale, groups=32):
+    _need_cuda(h, gamma_beta, out, control_scale)
+    call("supir_zerosft_apply", _ptr(h), h.stride(0), _ptr(skip_raw), 0 if skip_raw is None else skip_raw.stride(0), C1,
+         _ptr(gamma_beta), gamma_beta.stride(0), _ptr(out), out.stride(0), B, HW, h.shape[1], groups, _ptr(sums),
+         _ptr(gn_w), _ptr(gn_b), float(eps), _ptr(control_scale), _stream())
+    return out
+
+
+def layernorm(x, out, gamma, beta, eps=1e-5):
+    _need_cuda(x, out)
+    _mat(x), _mat(out)
+    call("supir_layernorm_bf16", _ptr(x), x.stride(0), _ptr(out), out.stride(0), x.shape[0], x.shape[1], _ptr(gamma),
+         _ptr(beta), float(eps), _stream())
+    return out
+
+
+def softmax_rows(S, P, cols, scale):
+    _need_cuda(S, P)
+    call("supir_softmax_rows", _ptr(S), S.stride(0), _ptr(P), P.stride(0), S.shape[0], cols, float(scale), _stream())
+    return P
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# small convs, data movement, embeddings
+# ------------------------------------------------------------------------------------------------------------------
+def conv3x3_small_cin(x_nchw, w, bias, out, residual=None):
+    """x_nchw: fp32 [B, Cin, H, W] view with unit stride along W; out NHWC bf16 [B*H*W, Cout]."""
+    _need_cuda(x_nchw, w, out)
+    B, Cin, H, W = x_nchw.shape
+    assert x_nchw.dtype == torch.float32 and x_nchw.stride(3) == 1 and w.dtype == torch.float32 and w.is_contiguous()
+    call("supir_conv3x3_small_cin", _ptr(x_nchw), x_nchw.stride(0), x_nchw.stride(1), x_nchw.stride(2), _ptr(w), _ptr(bias),
+         _ptr(residual), 0 if residual is None else residual.stride(0), _ptr(out), out.stride(0), B, H, W, Cin, out.shape[1],
+         _stream())
+    return out
+
+
+def conv3x3_small_cout(x, B, H, W, w, bias, out_nchw, crop=None):
+    """x NHWC bf16 [B*H*W, Cin]; out_nchw fp32 [B, Cout, h, w] view (unit stride along w) receiving the crop window."""
+    _need_cuda(x, w, out_nchw)
+    _mat(x)
+    y0, x0, ch, cw = crop if crop is not None else (0, 0, H, W)
+    assert out_nchw.dtype == torch.float32 and out_nchw.stride(3) == 1 and tuple(out_nchw.shape[2:]) == (ch, cw)
+    call("supir_conv3x3_small_cout", _ptr(x), x.stride(0), _ptr(w), _ptr(bias), _ptr(out_nchw), out_nchw.stride(0),
+         out_nchw.stride(1), out_nchw.stride(2), B, H, W, x.shape[1], out_nchw.shape[1], y0, x0, ch, cw, _stream())
+    return out_nchw
+
+
+def conv1x1_small_nchw(x, w, bias, out, in_scale=1.0):
+    _need_cuda(x, w, out)
+    assert x.is_contiguous() and out.is_contiguous() and x.dtype == torch.float32
+    B, Cin = x.shape[0], x.shape[1]
+    HW = x.numel() // (B * Cin)
+    call("supir_conv1x1_small_nchw", _ptr(x), _ptr(w), _ptr(bias), _ptr(out), B, Cin, out.shape[1], HW, float(in_scale), _stream())
+    return out
+
+
+def upsample2x(x, B, H, W, out):
+    call("supir_upsample_nearest2x", _ptr(x), x.stride(0), _ptr(out), out.stride(0), B, H, W, x.shape[1], _stream())
+    return out
+
+
+def im2col_s2(x, B, H, W, out, Ho, Wo, pad_lo):
+    assert out.is_contiguous() and out.shape == (B * Ho * Wo, 9 * x.shape[1])
+    call("supir_im2col_3x3_s2", _ptr(x), x.stride(0), _ptr(out), B, H, W, x.shape[1], Ho, Wo, pad_lo, _stream())
+    return out
+
+
+def copy2d(src, dst):
+    call("supir_copy2d_bf16", _ptr(src), src.stride(0), _ptr(dst), dst.stride(0), src.shape[0], src.shape[1], _stream())
+    return dst
+
+
+def axpy(a, y, out, scale):
+    call("supir_axpy_bf16", _ptr(a), a.stride(0), _ptr(y), y.stride(0), _ptr(out), out.stride(0), a.shape[0], a.shape[1],
+         _ptr(scale), _stream())
+    return out
+
+
+def nchw_f32_to_nhwc_bf16(x, out):
+    B, C = x.shape[0], x.shape[1]
+    assert x.is_contiguous() and x.dtype == torch.float32
+    call("supir_nchw_f32_to_nhwc_bf16", _ptr(x), _ptr(out), out.stride(0), B, C, x.numel() // (B * C), _stream())
+    return out
+
+
+def nhwc_bf16_to_nchw_f32(x, B, C, HW, out):
+    assert out.is_contiguous() and out.dtype == torch.float32
+    call("supir_nhwc_bf16_to_nchw_f32", _ptr(x), x.stride(0), _ptr(out), B, C, HW, _stream())
+    return out
+
+
+def f32_to_bf16(x, out):
+    assert x.is_contiguous() and out.is_contiguous()
+    call("supir_f32_to_bf16", _ptr(x), _ptr(out), x.numel(), _stream())
+    return out
+
+
+def timestep_embedding(t, out):
+    call("supir_timestep_embedding", _ptr(t), _ptr(out), out.shape[0], out.shape[1], _stream())
+    return out
+
+
+def linear_small_m(x, w, bias, out, silu_in=False, silu_out=False, add=None):
+    _need_cuda(x, w, out)
+    assert x.dtype == torch.float32 and out.dtype == torch.float32 and w.dtype == BF16 and w.is_contiguous()
+    call("supir_linear_small_m", _ptr(x), x.stride(0), _ptr(w), _ptr(bias), _ptr(out), out.stride(0), x.shape[0], w.shape[0],
+         w.shape[1], int(silu_in), int(silu_out), _ptr(add), 0 if add is None else add.stride(0), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# sampler
+# ------------------------------------------------------------------------------------------------------------------
+def edm_pre(x, eps, noise_mul, c_in, x_hat, net_in):
+    _need_cuda(x, x_hat, net_in)
+    assert x.is_contiguous() and x_hat.is_contiguous() and net_in.is_contiguous() and net_in.numel() == 2 * x.numel()
+    call("supir_edm_pre", _ptr(x), _ptr(eps), float(noise_mul), float(c_in), _ptr(x_hat), _ptr(net_in), x.numel(), _stream())
+
+
+def edm_post(x_hat, net_out, x_center, c_out, cfg_scale, restore_mul, sigma_hat, dt, x_next, denoised=None):
+    _need_cuda(x_hat, net_out, x_next)
+    assert x_hat.is_contiguous() and net_out.is_contiguous() and x_next.is_contiguous()
+    assert x_center is None or x_center.is_contiguous()
+    call("supir_edm_post", _ptr(x_hat), _ptr(net_out), _ptr(x_center), float(c_out), float(cfg_scale), float(restore_mul),
+         float(sigma_hat), float(dt), _ptr(x_next), _ptr(denoised), x_hat.numel(), _stream())
+
+
+def axpby_f32(a, alpha, b, beta, out):
+    _need_cuda(a, out)
+    assert a.is_contiguous() and out.is_contiguous() and a.dtype == torch.float32 and (b is None or b.is_contiguous())
+    call("supir_axpby_f32", _ptr(a), float(alpha), _ptr(b), float(beta), _ptr(out), a.numel(), _stream())
+    return out
+
+
+def cfg_combine(x, scale, out):
+    _need_cuda(x, scale, out)
+    N = out.shape[0]
+    assert x.is_contiguous() and out.is_contiguous() and x.shape[0] == 2 * N and scale.dtype == torch.float32
+    call("supir_cfg_combine", _ptr(x), _ptr(scale), _ptr(out), N, out.numel() // N, _stream())
+    return out
+
+
+def tile_gather(src, windows, tile, out):
+    """out[j, n, c] = src[n, c, window j]; src fp32 [N, C, H, W]; out fp32 [nw, N, C, tile, tile]."""
+    _need_cuda(src, windows, out)
+    assert src.is_contiguous() and out.is_contiguous() and windows.dtype == torch.int32 and src.dtype == torch.float32
+    N, C, H, W = src.shape
+    call("supir_tile_gather", _ptr(src), _ptr(windows), windows.shape[0], tile, _ptr(out), N, C, H, W, _stream())
+    return out
+
+
+def tile_blend(tiles, windows, tile, weights, out):
+    """tiles fp32 [nw, N, C, tile, tile]; windows int32 [nw, 4]; weights fp64 [tile, tile]; out fp32 [N, C, H, W]."""
+    _need_cuda(tiles, windows, weights, out)
+    assert tiles.is_contiguous() and out.is_contiguous() and windows.dtype == torch.int32 and weights.dtype == torch.float64
+    N, C, H, W = out.shape
+    call("supir_tile_blend", _ptr(tiles), _ptr(windows), windows.shape[0], tile, _ptr(weights), _ptr(out), N, C, H, W, _stream())
+    return out
+
+
+def gaussian_latent(moments, eps, scale, z):
+    B, C2 = moments.shape[0], moments.shape[1]
+    assert moments.is_contiguous() and z.is_contiguous()
+    call("supir_gaussian_latent", _ptr(moments), _ptr(eps), float(scale), _ptr(z), B, C2 // 2, moments.numel() // (B * C2), _stream())
+    return z

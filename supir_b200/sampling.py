@@ -1,0 +1,281 @@
+"""EDM Euler samplers of SUPIR (reference: sgm/modules/diffusionmodules/sampling.py:25-75, 528-660, 733-766).
+
+`RestoreEDMSampler` / `TiledRestoreEDMSampler` keep the reference constructor and call signatures. What differs is HOW a
+step runs:
+  * every sigma-dependent scalar (gamma, sigma_hat, c_in, c_out, CFG scale, restore factor, dt, linear control scale) is
+    computed on the host in float32 from the schedule, so a step has NO device->host sync (the reference has >= 2);
+  * the per-step latent arithmetic is two fused kernels (supir_edm_pre / supir_edm_post) around one CUDA-graph replay of
+    the control + UNet pair, when the denoiser is this package's (`FusedDenoiser`); a generic callable still works through
+    the unfused kernels;
+  * the tiled sampler stacks several windows into one network batch, and, under torch.distributed, shards the windows
+    over ranks with ONE all-gather of the window outputs per step; the Gaussian blend then runs on every rank in the
+    reference's window order (bit-identical x_{t+1} on all ranks; sampling.py:629-659).
+RNG stays in PyTorch (torch.randn_like in the reference's order); kernels take the noise as an input.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+from .config import instantiate_from_config
+
+SIGMA_MAX = 14.6146
+f32 = np.float32
+DEFAULT_GUIDER = {"target": "sgm.modules.diffusionmodules.guiders.IdentityGuider"}
+
+
+def gaussian_weights(tile_width, tile_height, nbatches, device="cuda"):
+    """sampling.py:733-750 (float64; x midpoint (W-1)/2, y midpoint H/2 — the reference's asymmetry is kept)."""
+    from numpy import exp, pi, sqrt
+    var = 0.01
+    midpoint = (tile_width - 1) / 2
+    x_probs = [exp(-(x - midpoint) * (x - midpoint) / (tile_width * tile_width) / (2 * var)) / sqrt(2 * pi * var)
+               for x in range(tile_width)]
+    midpoint = tile_height / 2
+    y_probs = [exp(-(y - midpoint) * (y - midpoint) / (tile_height * tile_height) / (2 * var)) / sqrt(2 * pi * var)
+               for y in range(tile_height)]
+    weights = np.outer(y_probs, x_probs)
+    return torch.tile(torch.tensor(weights, device=device), (nbatches, 4, 1, 1))
+
+
+def _sliding_windows(h: int, w: int, tile_size: int, tile_stride: int):
+    """sampling.py:753-766: (hi, hi_end, wi, wi_end) per window, row-major, last window clamped to the border."""
+    def starts(n):
+        s = list(range(0, n - tile_size + 1, tile_stride))
+        if (n - tile_size) % tile_stride != 0:
+            s.append(n - tile_size)
+        return s
+    return [(hi, hi + tile_size, wi, wi + tile_size) for hi in starts(h) for wi in starts(w)]
+
+
+def shard_windows(num_windows, world_size, rank):
+    """Contiguous block partition: rank r owns slots [r*per, (r+1)*per) of a table padded to per*world_size slots.
+    Contiguity keeps the slot order equal to the reference's window order, which the ordered blend relies on."""
+    per = (num_windows + world_size - 1) // world_size
+    lo = min(rank * per, num_windows)
+    hi = min(lo + per, num_windows)
+    return per, lo, hi
+
+
+def exchange_window_outputs(tiles_out, rank, per):
+    """The one collective of a tiled step: in-place all-gather of the per-rank blocks of `tiles_out`
+    ([world*per, ...] fp32, rank r owns slots [r*per, (r+1)*per)). NCCL on GPUs, gloo in the CPU tests."""
+    import torch.distributed as dist
+    mine = tiles_out[rank * per:(rank + 1) * per].reshape(-1).clone()
+    dist.all_gather_into_tensor(tiles_out.view(-1), mine)
+    return tiles_out
+
+
+class FusedDenoiser:
+    """Callable handed to the samplers by supir_b200.model.SUPIRModel: behaves like the reference's lambda
+    (SUPIR_model.py:123-125) and additionally exposes the parts so the sampler can fuse the step arithmetic."""
+
+    def __init__(self, denoiser, network):
+        self.denoiser, self.network = denoiser, network
+
+    def __call__(self, input, sigma, c, control_scale):
+        return self.denoiser(self.network, input, sigma, c, control_scale)
+
+
+class BaseDiffusionSampler:
+    def __init__(self, discretization_config, num_steps=None, guider_config=None, verbose=False, device="cuda"):
+        self.num_steps = num_steps
+        self.discretization = instantiate_from_config(discretization_config)
+        self.guider = instantiate_from_config(guider_config if guider_config is not None else DEFAULT_GUIDER)
+        self.verbose = verbose
+        self.device = device
+
+    def host_sigmas(self, num_steps=None):
+        s = self.discretization(self.num_steps if num_steps is None else num_steps, device="cpu")
+        return s.numpy().astype(np.float32)
+
+
+class RestoreEDMSampler(BaseDiffusionSampler):
+    def __init__(self, s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0, restore_cfg=4.0, restore_cfg_s_tmin=0.05,
+                 *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.s_churn, self.s_tmin, self.s_tmax, self.s_noise = s_churn, s_tmin, s_tmax, s_noise
+        self.restore_cfg, self.restore_cfg_s_tmin = restore_cfg, restore_cfg_s_tmin
+        self.sigma_max = SIGMA_MAX
+
+    # ---- host-side step constants, evaluated in float32 exactly where the reference uses float32 tensors ----
+    def step_constants(self, sigmas, i, control_scale, use_linear_control_scale, control_scale_start):
+        n = len(sigmas) - 1
+        sigma, next_sigma = f32(sigmas[i]), f32(sigmas[i + 1])
+        gamma = min(self.s_churn / n, 2 ** 0.5 - 1) if self.s_tmin <= sigma <= self.s_tmax else 0.0
+        sigma_hat = f32(sigma * f32(gamma + 1.0))
+        noise_mul = 0.0
+        if gamma > 0:
+            noise_mul = float(f32(self.s_noise) * f32(np.sqrt(f32(sigma_hat * sigma_hat - sigma * sigma))))
+        cs = control_scale
+        if use_linear_control_scale:
+            cs = (float(sigma) / self.sigma_max) * (control_scale_start - control_scale) + control_scale
+        restore_mul = 0.0
+        use_restore = (next_sigma > self.restore_cfg_s_tmin) and (self.restore_cfg > 0)
+        if use_restore:
+            restore_mul = float(f32(sigma / f32(self.sigma_max)) ** f32(self.restore_cfg))
+        return dict(sigma=float(sigma), next_sigma=float(next_sigma), gamma=gamma, sigma_hat=float(sigma_hat),
+                    noise_mul=noise_mul, control_scale=cs, use_restore=bool(use_restore), restore_mul=restore_mul,
+                    dt=float(f32(next_sigma - sigma_hat)))
+
+    # ---- one step on a batch of latents (x: fp32 [N,4,h,w]); eps may be None when gamma == 0 ----
+    def _step(self, denoiser, x, eps, cond, uc, x_center, k):
+        N = x.shape[0]
+        sig_hat_t = torch.full((N,), k["sigma_hat"], dtype=torch.float32, device=x.device)
+        if isinstance(denoiser, FusedDenoiser) and hasattr(self.guider, "scale_host"):
+            den = denoiser.denoiser
+            sq, idx = den.quantize_host(k["sigma_hat"])
+            c_in = float(f32(1.0) / np.sqrt(f32(sq) * f32(sq) + f32(1.0)))
+            x_hat = torch.empty_like(x)
+            net_in = torch.empty((2 * N,) + tuple(x.shape[1:]), dtype=torch.float32, device=x.device)
+            ops.edm_pre(x, eps if k["gamma"] > 0 else None, k["noise_mul"], c_in, x_hat, net_in)
+            cpair = {key: torch.cat((uc[key], cond[key]), 0) for key in ("vector", "crossattn", "control")}
+            t = torch.full((2 * N,), idx, dtype=torch.long, device=x.device)
+            net_out = denoiser.network(net_in, t, cpair, k["control_scale"])
+            x_next = torch.empty_like(x)
+            ops.edm_post(x_hat, net_out, x_center if k["use_restore"] else None, -sq, self.guider.scale_host(k["sigma_hat"]),
+                         k["restore_mul"], k["sigma_hat"], k["dt"], x_next)
+            return x_next
+        # generic callable (e.g. the reference's own denoiser lambda): unfused kernels, same arithmetic
+        x_hat = x
+        if k["gamma"] > 0:
+            x_hat = torch.empty_like(x)
+            ops.axpby_f32(x, 1.0, eps, k["noise_mul"], x_hat)
+        xi, si, ci = self.guider.prepare_inputs(x_hat, sig_hat_t, cond, uc)
+        denoised = self.guider(denoiser(xi, si, ci, k["control_scale"]), sig_hat_t).contiguous()
+        if k["use_restore"]:
+            d2 = torch.empty_like(denoised)
+            ops.axpby_f32(denoised, 1.0 - k["restore_mul"], x_center.contiguous(), k["restore_mul"], d2)
+            denoised = d2
+        r = k["dt"] / k["sigma_hat"]
+        x_next = torch.empty_like(x)
+        ops.axpby_f32(x_hat.contiguous(), 1.0 + r, denoised, -r, x_next)
+        return x_next
+
+    def prepare_sampling_loop(self, x, num_steps=None):
+        sigmas = self.host_sigmas(num_steps)
+        x0 = torch.empty_like(x, dtype=torch.float32)
+        ops.axpby_f32(x.contiguous().float(), float(np.sqrt(f32(1.0) + sigmas[0] * sigmas[0])), None, 0.0, x0)
+        return x0, sigmas
+
+    @torch.no_grad()
+    def __call__(self, denoiser, x, cond, uc=None, num_steps=None, x_center=None, control_scale=1.0,
+                 use_linear_control_scale=False, control_scale_start=0.0):
+        uc = cond if uc is None else uc
+        x, sigmas = self.prepare_sampling_loop(x, num_steps)
+        xc = None if x_center is None else x_center.contiguous().float()
+        for i in range(len(sigmas) - 1):
+            k = self.step_constants(sigmas, i, control_scale, use_linear_control_scale, control_scale_start)
+            eps = torch.randn_like(x) if k["gamma"] > 0 else None
+            x = self._step(denoiser, x, eps, cond, uc, xc, k)
+        return x
+
+
+class TiledRestoreEDMSampler(RestoreEDMSampler):
+    def __init__(self, tile_size=128, tile_stride=64, tile_batch=4, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.tile_size, self.tile_stride = tile_size, tile_stride
+        self.tile_batch = max(1, int(tile_batch))        # windows stacked into one network call
+        self._weights = None
+
+    @property
+    def tile_weights(self):
+        if self._weights is None:
+            self._weights = gaussian_weights(self.tile_size, self.tile_size, 1, device=self.device)
+        return self._weights
+
+    @torch.no_grad()
+    def __call__(self, denoiser, x, cond, uc=None, num_steps=None, x_center=None, control_scale=1.0,
+                 use_linear_control_scale=False, control_scale_start=0.0):
+        run = self.begin(denoiser, x, cond, uc, num_steps, x_center, control_scale, use_linear_control_scale,
+                         control_scale_start)
+        for i in range(run.num_steps):
+            run.step(i)
+        return run.x
+
+    @torch.no_grad()
+    def begin(self, denoiser, x, cond, uc=None, num_steps=None, x_center=None, control_scale=1.0,
+              use_linear_control_scale=False, control_scale_start=0.0):
+        """Set up a tiled run and return an object whose .step(i) advances one EDM step (bench.py times those)."""
+        return _TiledRun(self, denoiser, x, cond, uc, num_steps, x_center, control_scale, use_linear_control_scale,
+                         control_scale_start)
+
+
+class _TiledRun:
+    def __init__(self, smp, denoiser, x, cond, uc, num_steps, x_center, control_scale, use_linear_control_scale,
+                 control_scale_start):
+        import torch.distributed as dist
+        self.smp, self.denoiser, self.cond = smp, denoiser, cond
+        self.control_scale, self.lin_cs, self.cs_start = control_scale, use_linear_control_scale, control_scale_start
+        self.use_local_prompt = isinstance(cond, list)
+        b, ch, h, w = x.shape
+        T = smp.tile_size
+        windows = _sliding_windows(h, w, T, smp.tile_stride)
+        nw = len(windows)
+        if self.use_local_prompt:
+            assert len(cond) == nw, "Number of local prompts should be equal to number of tiles"
+            lq = cond[0]["control"]
+        else:
+            lq = cond["control"]
+        self.uc = (cond[0] if self.use_local_prompt else cond) if uc is None else uc
+        lq = lq.contiguous().float()
+        xc = x_center.contiguous().float()
+        self.world, self.rank = ((dist.get_world_size(), dist.get_rank())
+                                 if dist.is_available() and dist.is_initialized() else (1, 0))
+        self.per, self.lo, self.hi = shard_windows(nw, self.world, self.rank)
+        slots = self.per * self.world
+        table = torch.full((slots, 4), -1, dtype=torch.int32)
+        table[:nw] = torch.tensor(windows, dtype=torch.int32)
+        self.table_dev = table.to(x.device)
+        self.my_table = self.table_dev[self.lo:self.hi].contiguous()
+        self.weights64 = smp.tile_weights[0, 0].contiguous()
+        self.x, self.sigmas = smp.prepare_sampling_loop(x, num_steps)
+        self.num_steps = len(self.sigmas) - 1
+        self.shape = (b, ch, T)
+        self.tiles_out = torch.zeros((slots, b, ch, T, T), dtype=torch.float32, device=x.device)
+        self.n_mine = self.hi - self.lo
+        if self.n_mine > 0:     # per-window conditioning is constant across steps: gather it once
+            self.lq_t = torch.empty((self.n_mine, b, ch, T, T), dtype=torch.float32, device=x.device)
+            self.xc_t = torch.empty_like(self.lq_t)
+            ops.tile_gather(lq, self.my_table, T, self.lq_t)
+            ops.tile_gather(xc, self.my_table, T, self.xc_t)
+
+    @torch.no_grad()
+    def step(self, i, eps_noise=None):
+        import torch.distributed as dist
+        smp, x = self.smp, self.x
+        b, ch, T = self.shape
+        n_mine, lo = self.n_mine, self.lo
+        cond, uc = self.cond, self.uc
+        k = smp.step_constants(self.sigmas, i, self.control_scale, self.lin_cs, self.cs_start)
+        if eps_noise is None:
+            eps_noise = torch.randn_like(x)     # drawn every step, on every rank, like the reference (sampling.py:631)
+        if n_mine > 0:
+            x_t = torch.empty((n_mine, b, ch, T, T), dtype=torch.float32, device=x.device)
+            ops.tile_gather(x, self.my_table, T, x_t)
+            e_t = None
+            if k["gamma"] > 0:
+                e_t = torch.empty_like(x_t)
+                ops.tile_gather(eps_noise, self.my_table, T, e_t)
+            for g0 in range(0, n_mine, smp.tile_batch):
+                g1 = min(g0 + smp.tile_batch, n_mine)
+                g = g1 - g0
+
+                def stack(key):
+                    return torch.cat([(cond[lo + j] if self.use_local_prompt else cond)[key] for j in range(g0, g1)], 0)
+                c_g = {"control": self.lq_t[g0:g1].reshape(g * b, ch, T, T), "crossattn": stack("crossattn"),
+                       "vector": stack("vector")}
+                uc_g = {"control": c_g["control"], "crossattn": torch.cat([uc["crossattn"]] * g, 0),
+                        "vector": torch.cat([uc["vector"]] * g, 0)}
+                out = smp._step(self.denoiser, x_t[g0:g1].reshape(g * b, ch, T, T),
+                                None if e_t is None else e_t[g0:g1].reshape(g * b, ch, T, T), c_g, uc_g,
+                                self.xc_t[g0:g1].reshape(g * b, ch, T, T), k)
+                self.tiles_out[lo + g0:lo + g1] = out.view(g, b, ch, T, T)
+        if self.world > 1:
+            # the ONE exchange of a step: every rank receives all window outputs (NCCL all-gather over NVLink)
+            exchange_window_outputs(self.tiles_out, self.rank, self.per)
+        x_next = torch.empty_like(x)
+        ops.tile_blend(self.tiles_out, self.table_dev, T, self.weights64, x_next)
+        self.x = x_next
+        return x_next

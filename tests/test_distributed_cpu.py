@@ -1,0 +1,69 @@
+"""world_size-2 gloo test of the multi-GPU plumbing on CPU: window sharding + the per-step all-gather reproduce the
+single-process result of the reference's sequential blend bit-for-bit."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _blend_reference_order(tiles, windows, weights64, shape):
+    """sampling.py:656-659 in the reference's order (the oracle of supir_tile_blend)."""
+    x_next, count = torch.zeros(shape), torch.zeros(shape)
+    tw = weights64.repeat(shape[0], shape[1], 1, 1)
+    for j, (hi, he, wi, we) in enumerate(windows):
+        if hi < 0:
+            continue
+        x_next[:, :, hi:he, wi:we] += tiles[j] * tw
+        count[:, :, hi:he, wi:we] += tw
+    x_next /= count
+    return x_next
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    from oracle import sampler as osamp
+    from supir_b200.sampling import _sliding_windows, exchange_window_outputs, shard_windows
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    N, C, H, W, T = 1, 4, 40, 28, 16
+    windows = _sliding_windows(H, W, T, 8)
+    nw = len(windows)
+    per, lo, hi = shard_windows(nw, world, rank)
+    g = torch.Generator().manual_seed(7)
+    all_tiles = torch.randn((nw, N, C, T, T), generator=g)      # what a single process would compute
+    tiles_out = torch.zeros((per * world, N, C, T, T))
+    tiles_out[lo:hi] = all_tiles[lo:hi]                         # this rank computes only its windows
+    exchange_window_outputs(tiles_out, rank, per)
+    table = [(-1, -1, -1, -1)] * (per * world)
+    table[:nw] = windows
+    w64 = torch.tensor(osamp.gaussian_weights(T, T))
+    got = _blend_reference_order(tiles_out, table, w64, (N, C, H, W))
+    want = _blend_reference_order(all_tiles, windows, w64, (N, C, H, W))
+    q.put((rank, bool(torch.equal(got, want)), bool(torch.equal(tiles_out[:nw], all_tiles))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_sharded_windows_all_gather_equals_single_process(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r[0] for r in res) == list(range(world))
+    assert all(r[1] and r[2] for r in res), res

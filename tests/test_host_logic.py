@@ -1,0 +1,140 @@
+"""CPU tests: C-ABI library loads and exports every declared symbol; host-side integer bookkeeping and float32 schedule
+of the product (supir_b200) equal the reference's golden values; the product refuses to run without CUDA."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def bits(t):
+    return np.asarray(t, dtype=np.float32).view(np.uint32).tolist()
+
+
+@pytest.fixture(scope="module")
+def book():
+    with open(os.path.join(G, "bookkeeping.json")) as f:
+        return json.load(f)
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from supir_b200 import _native
+    lib = _native.load()
+    header = open(os.path.join(ROOT, "include", "supir_b200.h")).read()
+    declared = set(re.findall(r"\b(supir_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 35
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/supir_b200.h but not exported"
+    assert declared == set(_native.EXPORTED_SYMBOLS), declared ^ set(_native.EXPORTED_SYMBOLS)
+    assert lib.supir_version() >= 100
+    assert lib.supir_last_error() is not None
+
+
+def test_no_cpu_fallback():
+    from supir_b200 import _native, ops
+    with pytest.raises(_native.SupirNativeError):
+        ops.gemm(torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(8, 8, dtype=torch.bfloat16))
+    from supir_b200 import vae
+    with torch.device("meta"):
+        pass
+    enc_cfg = dict(ch=32, out_ch=3, ch_mult=[1, 2], num_res_blocks=1, attn_resolutions=[], in_channels=3, resolution=32, z_channels=4)
+    with pytest.raises(RuntimeError):
+        vae.Encoder(**enc_cfg)(torch.zeros(1, 3, 16, 16))
+
+
+def test_product_windows_tiles_and_schedule_match_reference(book):
+    from supir_b200 import denoiser as dn, sampling, vae
+    for case in book["sliding_windows"]:
+        assert [list(c) for c in sampling._sliding_windows(*case["args"])] == case["windows"]
+    for case, crop in zip(book["split_tiles"], book["crop"]):
+        h, w, tile, dec = case["args"]
+        ib, ob = vae.split_tiles(h, w, tile, dec)
+        assert ib == case["in"] and ob == case["out"]
+        for i, o, ref in zip(ib, ob, crop["crops"]):
+            th, tw = (i[3] - i[2]), (i[1] - i[0])
+            th, tw = (th * 8, tw * 8) if dec else (th // 8, tw // 8)
+            y0, y1, x0, x1 = vae.crop_margins(th, tw, i, o, dec)
+            idx = torch.arange(th * tw).view(th, tw)[y0:y1, x0:x1]
+            assert [int(idx[0, 0]), int(idx[-1, -1]), idx.shape[0], idx.shape[1]] == ref
+    for lb, ub, ref in book["best_tile"]:
+        assert vae.get_best_tile_size(lb, ub) == ref
+    disc = dn.LegacyDDPMDiscretization()
+    for n, ref in book["sigmas"].items():
+        assert bits(disc(int(n)).numpy()) == ref
+    den = dn.DiscreteDenoiserWithControl(
+        weighting_config={"target": "sgm.modules.diffusionmodules.denoiser_weighting.EpsWeighting"},
+        scaling_config={"target": "sgm.modules.diffusionmodules.denoiser_scaling.EpsScaling"}, num_idx=1000,
+        discretization_config={"target": "sgm.modules.diffusionmodules.discretizer.LegacyDDPMDiscretization"})
+    assert bits(den.sigmas.numpy()) == book["denoiser_table"]
+    probe = np.array(book["sigma_to_idx"]["sigma"], dtype=np.uint32).view(np.float32)
+    assert [den.quantize_host(float(s))[1] for s in probe] == book["sigma_to_idx"]["idx"]
+    assert den.sigma_to_idx(torch.tensor(probe)).tolist() == book["sigma_to_idx"]["idx"]
+    g = np.load(os.path.join(G, "gaussian_weights.npz"))
+    assert np.array_equal(sampling.gaussian_weights(128, 128, 1, device="cpu").numpy(), g["w128"])
+    assert np.array_equal(sampling.gaussian_weights(16, 24, 2, device="cpu").numpy(), g["w16x24"])
+
+
+def test_step_constants_match_oracle_arithmetic():
+    """The host-side float32 scalars of a step equal what the oracle computes with float32 tensors."""
+    from oracle import sampler as osamp
+    from supir_b200 import sampling
+    guider = {"target": "sgm.modules.diffusionmodules.guiders.LinearCFG", "params": {"scale": 1.0, "scale_min": 4.0}}
+    smp = sampling.RestoreEDMSampler(num_steps=50, restore_cfg=4.0, s_churn=5, s_noise=1.01, guider_config=guider,
+                                     discretization_config={"target": "sgm.modules.diffusionmodules.discretizer.LegacyDDPMDiscretization"})
+    sig = smp.host_sigmas()
+    ref = osamp.legacy_ddpm_sigmas(50)
+    assert bits(sig) == bits(ref.numpy())
+    for i in (0, 1, 17, 48, 49):
+        k = smp.step_constants(sig, i, 0.9, True, 0.2)
+        s, ns = ref[i:i + 1], ref[i + 1:i + 2]
+        gamma = min(5 / 50, 2 ** 0.5 - 1)
+        sh = s * (gamma + 1.0)
+        assert np.float32(k["sigma_hat"]) == sh.numpy()[0]
+        assert np.float32(k["dt"]) == (ns - sh).numpy()[0]
+        nm = (1.01 * ((sh ** 2 - s ** 2) ** 0.5)).numpy()[0]
+        assert abs(k["noise_mul"] - nm) <= 1e-6 * nm
+        assert k["use_restore"] == bool(ns[0] > 0.05)
+        if k["use_restore"]:
+            assert abs(k["restore_mul"] - float((s / 14.6146) ** 4.0)) <= 1e-6
+        assert abs(smp.guider.scale_host(k["sigma_hat"]) - float(osamp.linear_cfg_scale(1.0, 4.0, sh)[0])) <= 1e-6
+        assert abs(k["control_scale"] - ((float(s[0]) / 14.6146) * (0.2 - 0.9) + 0.9)) <= 1e-7
+
+
+def test_shard_windows_partition():
+    from supir_b200.sampling import shard_windows
+    for nw in (1, 7, 49, 64, 225):
+        for world in (1, 2, 4, 8):
+            seen = []
+            for r in range(world):
+                per, lo, hi = shard_windows(nw, world, r)
+                assert 0 <= lo <= hi <= nw and hi - lo <= per
+                seen += list(range(lo, hi))
+            assert seen == list(range(nw))          # contiguous, ordered, complete
+
+
+def test_state_dict_keys_match_reference_fixture():
+    """Key names/shapes of the product's modules equal the reference's (fixtures were dumped from the reference)."""
+    from supir_b200 import nets, vae, wrappers
+    g = np.load(os.path.join(G, "unet_fullwidth_depth1.npz"))
+    cfg, shapes = json.loads(str(g["cfg"])), json.loads(str(g["shapes"]))
+    with torch.device("meta"):
+        w = wrappers.ControlWrapper(nets.LightGLVUNet(mode="XL-base", project_type="ZeroSFT", project_channel_scale=2, **cfg))
+        w.load_control_model(nets.GLVControl(input_upscale=1, **cfg))
+    assert {k: list(v.shape) for k, v in w.state_dict().items()} == shapes
+    g = np.load(os.path.join(G, "vae_tiny.npz"))
+    with torch.device("meta"):
+        ae = vae.AutoencoderKLInferenceWrapper(embed_dim=4, ddconfig=json.loads(str(g["cfg"])), lossconfig={"target": "torch.nn.Identity"})
+    assert {k: list(v.shape) for k, v in ae.state_dict().items()} == json.loads(str(g["shapes"]))
+
+
+def test_config_factory_resolves_reference_targets():
+    from supir_b200 import config
+    cfg = config.load_yaml(os.path.join(ROOT, "tests", "golden", "SUPIR_v0_tiled_sampler.yaml"))
+    smp = config.instantiate_from_config(dict(cfg["sampler_config"], params=dict(cfg["sampler_config"]["params"], device="cpu")))
+    assert type(smp).__name__ == "TiledRestoreEDMSampler" and type(smp).__module__ == "supir_b200.sampling"
+    assert smp.tile_size == 128 and smp.tile_stride == 64 and type(smp.guider).__name__ == "LinearCFG"
