@@ -4,15 +4,19 @@
 // (sgm/modules/attention.py:273-277, 357-359) for self-attention, 77-token cross-attention and ZeroCrossAttn
 // (SUPIR/modules/SUPIR_v0.py:146).
 //
-// One CTA = one (batch, head, 128-query block); 192 threads:
-//   warp 0 lane 0 : TMA producer (Q once; K/V 128-row blocks through a 3-stage ring)
-//   warp 1 lane 0 : tcgen05.mma issuer:  S_j = Q K_j^T  (128x128x64)  -> TMEM S[j&1]
-//                                        O_j = P_j V_j   (128x64x128)  -> TMEM O[j&1]   (not accumulated in TMEM)
-//   warps 2..5    : one query row per thread. Pass 1 over S: row max; pass 2: p = exp2((s - m) * scale), row sum, P written
-//                   to shared memory as the bf16 K-major 128B-swizzled A operand of the PV MMA; the running output is
-//                   kept in registers: O = (O + O_{j-1}) * alpha_j, so the rescale never touches TMEM.
-// QK^T of block j+1 is issued before PV of block j, so the tensor pipe works while the softmax warps are busy.
-// V is consumed in its natural [kv, d] layout as an MN-major B operand (no transpose pass).
+// One CTA = one (batch, head) and 256 queries = two 128-row tiles A and B; 320 threads:
+//   warp 0 lane 0 : TMA producer (Q_A, Q_B once; K/V 128-row blocks through a 3-stage ring, shared by both tiles)
+//   warp 1 lane 0 : tcgen05.mma issuer. Per tile X and key block j:
+//                     S_X = Q_X K_j^T   (128x128x64, TMEM, overwritten every block)
+//                     O_X += P_X V_j    (128x64x128, ACCUMULATED in TMEM across blocks)
+//                   with V consumed in its natural [kv, d] layout as an MN-major B operand.
+//   warps 2..5    : softmax group of tile A, warps 6..9: tile B — one query row per thread. The whole S row (128 fp32) is
+//                   read from TMEM once into registers; p = ex2((s - m) * scale) goes to shared memory as the bf16 K-major
+//                   128B-swizzled A operand of the PV MMA.
+// Online softmax without touching O every block: the exponent reference m is only moved when the running row maximum
+// exceeds it by more than 8 (p <= 2^8 stays exact enough in bf16/fp32); only then the warp rescales its 32 rows of O in
+// TMEM (tcgen05.ld / tcgen05.st) and its row sum. Two independent tiles keep the tensor pipe and the MUFU pipe busy
+// while the other tile waits on a dependency; the ex2 throughput (16/clk/SM) is this kernel's roofline, not the MMA.
 #include "common.cuh"
 #include "supir_b200.h"
 
@@ -21,11 +25,12 @@ namespace supir {
 int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
                    const uint32_t* box);
 
-static constexpr int ATT_BM = 128;   // queries per CTA
+static constexpr int ATT_BM = 128;   // queries per tile (two tiles per CTA)
 static constexpr int ATT_BN = 128;   // keys per block
 static constexpr int ATT_D = 64;
 static constexpr int ATT_STAGES = 3;
-static constexpr int ATT_THREADS = 192;
+static constexpr int ATT_THREADS = 320;
+static constexpr float ATT_RESCALE_THRESHOLD = 8.0f;   // log2 units
 
 struct AttnParams {
     int Lq, Lk, H;
@@ -38,12 +43,12 @@ struct AttnParams {
 };
 
 struct AttnSmem {
-    static constexpr int Q_BYTES = ATT_BM * ATT_D * 2;          // 16 KB
+    static constexpr int Q_BYTES = ATT_BM * ATT_D * 2;          // 16 KB per tile
     static constexpr int K_BYTES = ATT_BN * ATT_D * 2;          // 16 KB
     static constexpr int V_BYTES = ATT_BN * ATT_D * 2;          // 16 KB
-    static constexpr int P_BYTES = ATT_BM * ATT_BN * 2;         // 32 KB (two 64-column halves)
+    static constexpr int P_BYTES = ATT_BM * ATT_BN * 2;         // 32 KB per tile (two 64-column halves)
     static constexpr int OFF_Q = 0;
-    static constexpr int OFF_K = OFF_Q + Q_BYTES;
+    static constexpr int OFF_K = OFF_Q + 2 * Q_BYTES;
     static constexpr int OFF_V = OFF_K + ATT_STAGES * K_BYTES;
     static constexpr int OFF_P = OFF_V + ATT_STAGES * V_BYTES;
     static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
@@ -63,16 +68,16 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     uint64_t* q_full = bars;                // 1
     uint64_t* kv_full = bars + 1;           // [3]
     uint64_t* kv_empty = bars + 4;          // [3]
-    uint64_t* s_full = bars + 7;            // [2]
-    uint64_t* s_empty = bars + 9;           // [2]
-    uint64_t* p_full = bars + 11;           // [2]
-    uint64_t* o_full = bars + 13;           // [2]
-    uint64_t* o_empty = bars + 15;          // [2]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 17);
+    uint64_t* s_full = bars + 7;            // [2] per tile
+    uint64_t* p_full = bars + 9;            // [2] per tile
+    uint64_t* pv_done = bars + 11;          // [2] per tile
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qblk = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
     const int nblk = (p.Lk + ATT_BN - 1) / ATT_BN;
+    const int q0 = qblk * 2 * ATT_BM;                           // first query row of this CTA (within the batch element)
+    const bool tileB_valid = (q0 + ATT_BM) < p.Lq;               // CTA-uniform
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ);
@@ -82,10 +87,8 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int s = 0; s < ATT_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&s_full[i], 1);
-            mbar_init(&s_empty[i], 4);
             mbar_init(&p_full[i], 4);
-            mbar_init(&o_full[i], 1);
-            mbar_init(&o_empty[i], 4);
+            mbar_init(&pv_done[i], 1);
         }
         fence_barrier_init();
     }
@@ -97,14 +100,14 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
-    const uint32_t tS = tmem_base;          // S[i] at column i*128
-    const uint32_t tO = tmem_base + 256;    // O[i] at column 256 + i*64
+    // TMEM columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384)
 
     if (warp == 0) {
         if (lane == 0) {
             // ---------------- TMA producer ----------------
-            mbar_expect_tx(q_full, AttnSmem::Q_BYTES);
-            tma_load_2d(sQ, &tmQ, q_full, head * ATT_D, batch * p.Lq + qblk * ATT_BM);
+            mbar_expect_tx(q_full, (tileB_valid ? 2 : 1) * AttnSmem::Q_BYTES);
+            tma_load_2d(sQ, &tmQ, q_full, head * ATT_D, batch * p.Lq + q0);
+            if (tileB_valid) tma_load_2d(sQ + AttnSmem::Q_BYTES, &tmQ, q_full, head * ATT_D, batch * p.Lq + q0 + ATT_BM);
             int stage = 0;
             uint32_t phase = 0;
             for (int j = 0; j < nblk; ++j) {
@@ -119,155 +122,157 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if (lane == 0) {
             // ---------------- MMA issuer ----------------
             const uint64_t dtemplate = (uint64_t)p.desc_hi << 32;
-            const uint64_t qdesc = dtemplate | ((smem_u32(sQ) >> 4) & 0x3FFF);
-            mbar_wait(q_full, 0);
-            int stage = 0;
-            uint32_t kv_phase = 0;
-            int pv_stage = 0;
-            for (int j = 0; j <= nblk; ++j) {
-                if (j < nblk) {
-                    const int sb = j & 1;
-                    mbar_wait(&kv_full[stage], kv_phase);
-                    mbar_wait(&s_empty[sb], ((j >> 1) & 1) ^ 1);
-                    tc_fence_after();
-                    const uint64_t kdesc = dtemplate | ((smem_u32(sK + stage * AttnSmem::K_BYTES) >> 4) & 0x3FFF);
+            const int ntile = tileB_valid ? 2 : 1;
+            auto issue_qk = [&](int x, int stage) {
+                const uint64_t qdesc = dtemplate | ((smem_u32(sQ + x * AttnSmem::Q_BYTES) >> 4) & 0x3FFF);
+                const uint64_t kdesc = dtemplate | ((smem_u32(sK + stage * AttnSmem::K_BYTES) >> 4) & 0x3FFF);
 #pragma unroll
-                    for (int k = 0; k < ATT_D / 16; ++k)
-                        umma_bf16(tS + sb * ATT_BN, qdesc + 2 * k, kdesc + 2 * k, p.idesc_qk, k != 0);
-                    umma_commit(&s_full[sb]);
-                    if (++stage == ATT_STAGES) { stage = 0; kv_phase ^= 1; }
+                for (int k = 0; k < ATT_D / 16; ++k)
+                    umma_bf16(tmem_base + x * ATT_BN, qdesc + 2 * k, kdesc + 2 * k, p.idesc_qk, k != 0);
+                umma_commit(&s_full[x]);
+            };
+            mbar_wait(q_full, 0);
+            mbar_wait(&kv_full[0], 0);
+            tc_fence_after();
+            for (int x = 0; x < ntile; ++x) issue_qk(x, 0);
+            int stage = 0;                 // stage holding block j
+            uint32_t kv_phase = 0;
+            for (int j = 0; j < nblk; ++j) {
+                int nstage = stage + 1;
+                uint32_t nphase = kv_phase;
+                if (nstage == ATT_STAGES) { nstage = 0; nphase ^= 1; }
+                if (j + 1 < nblk) {
+                    mbar_wait(&kv_full[nstage], nphase);
                 }
-                if (j > 0) {
-                    const int jj = j - 1, ob = jj & 1;
-                    mbar_wait(&p_full[ob], (jj >> 1) & 1);
-                    mbar_wait(&o_empty[ob], ((jj >> 1) & 1) ^ 1);
+                for (int x = 0; x < ntile; ++x) {
+                    mbar_wait(&p_full[x], j & 1);       // P_X(j) written, S_X(j) consumed
                     tc_fence_after();
-                    const uint32_t pbase = smem_u32(sP + ob * AttnSmem::P_BYTES);
-                    const uint32_t vbase = smem_u32(sV + pv_stage * AttnSmem::V_BYTES);
+                    if (j + 1 < nblk) issue_qk(x, nstage);
+                    const uint32_t pbase = smem_u32(sP + x * AttnSmem::P_BYTES);
+                    const uint32_t vbase = smem_u32(sV + stage * AttnSmem::V_BYTES);
 #pragma unroll
                     for (int k = 0; k < ATT_BN / 16; ++k) {
                         // A = P: K-major, two 64-column halves of 16 KB, 32 B per 16-k step inside a half
                         const uint32_t pa = pbase + (k >> 2) * (AttnSmem::P_BYTES / 2) + (k & 3) * 32;
                         // B = V: MN-major (d contiguous), 16 kv rows of 128 B per step
                         const uint32_t va = vbase + k * 16 * 128;
-                        umma_bf16(tO + ob * ATT_D, dtemplate | ((pa >> 4) & 0x3FFF), dtemplate | ((va >> 4) & 0x3FFF),
-                                  p.idesc_pv, k != 0);
+                        umma_bf16(tmem_base + 256 + x * ATT_D, dtemplate | ((pa >> 4) & 0x3FFF),
+                                  dtemplate | ((va >> 4) & 0x3FFF), p.idesc_pv, (j | k) != 0);
                     }
-                    umma_commit(&o_full[ob]);
-                    umma_commit(&kv_empty[pv_stage]);
-                    if (++pv_stage == ATT_STAGES) pv_stage = 0;
+                    umma_commit(&pv_done[x]);
                 }
+                umma_commit(&kv_empty[stage]);
+                stage = nstage;
+                kv_phase = nphase;
             }
         }
     } else {
         // ---------------- softmax / output warps ----------------
-        const int quad = warp & 3;
-        const int row = quad * 32 + lane;                       // query row inside the tile
-        const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-        float o_acc[ATT_D];
-#pragma unroll
-        for (int i = 0; i < ATT_D; ++i) o_acc[i] = 0.f;
-        float m_run = -INFINITY, l_run = 0.f;
-        uint8_t* p_row_base = nullptr;
-        for (int j = 0; j < nblk; ++j) {
-            const int sb = j & 1;
-            mbar_wait(&s_full[sb], (j >> 1) & 1);
-            tc_fence_after();
-            const int kv_valid = min(ATT_BN, p.Lk - j * ATT_BN);
-            // pass 1: row max
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int c0 = 0; c0 < ATT_BN; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32(tS + sb * ATT_BN + lane_off + c0, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (c0 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r[i]));
-            }
-            const float m_new = fmaxf(m_run, mx * p.scale_log2);
-            const float alpha = exp2f(m_run - m_new);   // 0 on the first block (m_run = -inf)
-            // pass 2: probabilities -> P (bf16, swizzled K-major), row sum
-            float lsum = 0.f;
-            p_row_base = sP + sb * AttnSmem::P_BYTES + row * 128;
-#pragma unroll 1
-            for (int c0 = 0; c0 < ATT_BN; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32(tS + sb * ATT_BN + lane_off + c0, r);
-                tmem_ld_wait();
-                float pv[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float e = (c0 + i < kv_valid) ? exp2f(__uint_as_float(r[i]) * p.scale_log2 - m_new) : 0.f;
-                    pv[i] = e;
-                    lsum += e;
-                }
-                uint8_t* half_base = p_row_base + (c0 >> 6) * (AttnSmem::P_BYTES / 2);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int chunk = ((c0 & 63) >> 3) + q;            // 16-byte chunk index inside the 128-byte row
-                    uint4 u;
-                    u.x = pack_bf16x2(pv[q * 8 + 0], pv[q * 8 + 1]);
-                    u.y = pack_bf16x2(pv[q * 8 + 2], pv[q * 8 + 3]);
-                    u.z = pack_bf16x2(pv[q * 8 + 4], pv[q * 8 + 5]);
-                    u.w = pack_bf16x2(pv[q * 8 + 6], pv[q * 8 + 7]);
-                    *reinterpret_cast<uint4*>(half_base + ((chunk ^ (row & 7)) << 4)) = u;
-                }
-            }
-            tc_fence_before();
-            fence_proxy_async_smem();   // make the generic-proxy writes of P visible to the tensor-core (async) proxy
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&s_empty[sb]);
-                mbar_arrive(&p_full[sb]);
-            }
-            // fold in the previous block's PV product, then rescale to the new running max
-            if (j > 0) {
-                const int ob = (j - 1) & 1;
-                mbar_wait(&o_full[ob], ((j - 1) >> 1) & 1);
+        const int x = (warp - 2) >> 2;                          // tile 0 (A) or 1 (B)
+        if (x == 0 || tileB_valid) {
+            const int quad = warp & 3;
+            const int row = quad * 32 + lane;                   // query row inside the tile
+            const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+            const uint32_t tS = tmem_base + x * ATT_BN + lane_off;
+            const uint32_t tO = tmem_base + 256 + x * ATT_D + lane_off;
+            uint8_t* p_row = sP + x * AttnSmem::P_BYTES + row * 128;
+            float m_ref = 0.f, l_run = 0.f;
+            for (int j = 0; j < nblk; ++j) {
+                mbar_wait(&s_full[x], j & 1);
                 tc_fence_after();
-#pragma unroll
-                for (int c0 = 0; c0 < ATT_D; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(tO + ob * ATT_D + lane_off + c0, r);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) o_acc[c0 + i] += __uint_as_float(r[i]);
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&o_empty[ob]);
-            }
-#pragma unroll
-            for (int i = 0; i < ATT_D; ++i) o_acc[i] *= alpha;
-            l_run = l_run * alpha + lsum;
-            m_run = m_new;
-        }
-        {
-            const int ob = (nblk - 1) & 1;
-            mbar_wait(&o_full[ob], ((nblk - 1) >> 1) & 1);
-            tc_fence_after();
-#pragma unroll
-            for (int c0 = 0; c0 < ATT_D; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32(tO + ob * ATT_D + lane_off + c0, r);
+                uint32_t s[128];
+                tmem_ld_32x32(tS + 0, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+                tmem_ld_32x32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+                tmem_ld_32x32(tS + 64, *reinterpret_cast<uint32_t(*)[32]>(&s[64]));
+                tmem_ld_32x32(tS + 96, *reinterpret_cast<uint32_t(*)[32]>(&s[96]));
                 tmem_ld_wait();
+                const int kv_valid = min(ATT_BN, p.Lk - j * ATT_BN);
+                float mx = -INFINITY;
+                if (kv_valid == ATT_BN) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) o_acc[c0 + i] += __uint_as_float(r[i]);
+                    for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 128; ++i) {
+                        if (i >= kv_valid) s[i] = 0xff800000u;   // -inf
+                        mx = fmaxf(mx, __uint_as_float(s[i]));
+                    }
+                }
+                mx *= p.scale_log2;
+                // previous PV of this tile must have finished: it reads P (about to be overwritten) and updates O
+                if (j > 0) {
+                    mbar_wait(&pv_done[x], (j - 1) & 1);
+                    tc_fence_after();
+                }
+                if (j == 0) {
+                    m_ref = mx;
+                } else {
+                    const bool need = mx > m_ref + ATT_RESCALE_THRESHOLD;
+                    if (__any_sync(0xffffffffu, need)) {
+                        const float alpha = need ? ex2_approx(m_ref - mx) : 1.0f;
+                        if (need) m_ref = mx;
+                        l_run *= alpha;
+#pragma unroll
+                        for (int c0 = 0; c0 < ATT_D; c0 += 32) {
+                            uint32_t o[32];
+                            tmem_ld_32x32(tO + c0, o);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                            tmem_st_32x32(tO + c0, o);
+                        }
+                        tmem_st_wait();
+                    }
+                }
+                float lsum = 0.f;
+#pragma unroll
+                for (int c0 = 0; c0 < ATT_BN; c0 += 32) {
+                    uint8_t* half_base = p_row + (c0 >> 6) * (AttnSmem::P_BYTES / 2);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float e[8];
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) {
+                            e[t] = ex2_approx(fmaf(__uint_as_float(s[c0 + q * 8 + t]), p.scale_log2, -m_ref));
+                            lsum += e[t];
+                        }
+                        const int chunk = ((c0 & 63) >> 3) + q;         // 16-byte chunk index inside the 128-byte row
+                        uint4 u;
+                        u.x = pack_bf16x2(e[0], e[1]);
+                        u.y = pack_bf16x2(e[2], e[3]);
+                        u.z = pack_bf16x2(e[4], e[5]);
+                        u.w = pack_bf16x2(e[6], e[7]);
+                        *reinterpret_cast<uint4*>(half_base + ((chunk ^ (row & 7)) << 4)) = u;
+                    }
+                }
+                l_run += lsum;
+                tc_fence_before();
+                fence_proxy_async_smem();   // generic-proxy writes of P -> visible to the tensor-core (async) proxy
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[x]);
             }
-        }
-        const int qrow = qblk * ATT_BM + row;
-        if (qrow < p.Lq) {
+            // epilogue: O / l
+            mbar_wait(&pv_done[x], (nblk - 1) & 1);
+            tc_fence_after();
+            const int qrow = q0 + x * ATT_BM + row;
             const float inv = 1.f / l_run;
             __nv_bfloat16* dst = p.out + ((long long)batch * p.Lq + qrow) * p.ldo + head * ATT_D;
 #pragma unroll
-            for (int q = 0; q < ATT_D / 8; ++q) {
-                uint4 u;
-                u.x = pack_bf16x2(o_acc[q * 8 + 0] * inv, o_acc[q * 8 + 1] * inv);
-                u.y = pack_bf16x2(o_acc[q * 8 + 2] * inv, o_acc[q * 8 + 3] * inv);
-                u.z = pack_bf16x2(o_acc[q * 8 + 4] * inv, o_acc[q * 8 + 5] * inv);
-                u.w = pack_bf16x2(o_acc[q * 8 + 6] * inv, o_acc[q * 8 + 7] * inv);
-                reinterpret_cast<uint4*>(dst)[q] = u;
+            for (int c0 = 0; c0 < ATT_D; c0 += 32) {
+                uint32_t o[32];
+                tmem_ld_32x32(tO + c0, o);
+                tmem_ld_wait();
+                if (qrow < p.Lq) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint4 u;
+                        u.x = pack_bf16x2(__uint_as_float(o[q * 8 + 0]) * inv, __uint_as_float(o[q * 8 + 1]) * inv);
+                        u.y = pack_bf16x2(__uint_as_float(o[q * 8 + 2]) * inv, __uint_as_float(o[q * 8 + 3]) * inv);
+                        u.z = pack_bf16x2(__uint_as_float(o[q * 8 + 4]) * inv, __uint_as_float(o[q * 8 + 5]) * inv);
+                        u.w = pack_bf16x2(__uint_as_float(o[q * 8 + 6]) * inv, __uint_as_float(o[q * 8 + 7]) * inv);
+                        reinterpret_cast<uint4*>(dst + c0)[q] = u;
+                    }
+                }
             }
         }
     }
@@ -330,7 +335,7 @@ extern "C" int supir_attention_bf16(const void* q, long long ldq, const void* k,
     p.desc_hi = (uint32_t)(dt >> 32);
     p.idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN, 0, 0);
     p.idesc_pv = g_att_idesc_pv_override >= 0 ? (uint32_t)g_att_idesc_pv_override : umma_idesc_bf16(ATT_BM, ATT_D, 0, 1);
-    dim3 grid((Lq + ATT_BM - 1) / ATT_BM, H, B);
+    dim3 grid((Lq + 2 * ATT_BM - 1) / (2 * ATT_BM), H, B);
     attention_d64_kernel<<<grid, ATT_THREADS, AttnSmem::TOTAL, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
     count_launch();
     SUPIR_CHECK_CUDA(cudaGetLastError());
