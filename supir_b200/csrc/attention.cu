@@ -4,13 +4,14 @@
 // (sgm/modules/attention.py:273-277, 357-359) for self-attention, 77-token cross-attention and ZeroCrossAttn
 // (SUPIR/modules/SUPIR_v0.py:146).
 //
-// One CTA = one (batch, head) and 256 queries = two 128-row tiles A and B; 320 threads:
+// One CTA = one (batch, head) and 256 queries = two 128-row tiles A and B; 384 threads (3 warpgroups; the softmax
+// warpgroups take the registers the control warpgroup gives up via setmaxnreg, so a whole S row lives in registers):
 //   warp 0 lane 0 : TMA producer (Q_A, Q_B once; K/V 128-row blocks through a 3-stage ring, shared by both tiles)
 //   warp 1 lane 0 : tcgen05.mma issuer. Per tile X and key block j:
 //                     S_X = Q_X K_j^T   (128x128x64, TMEM, overwritten every block)
 //                     O_X += P_X V_j    (128x64x128, ACCUMULATED in TMEM across blocks)
 //                   with V consumed in its natural [kv, d] layout as an MN-major B operand.
-//   warps 2..5    : softmax group of tile A, warps 6..9: tile B — one query row per thread. The whole S row (128 fp32) is
+//   warps 4..7    : softmax group of tile A, warps 8..11: tile B — one query row per thread. The whole S row (128 fp32) is
 //                   read from TMEM once into registers; p = ex2((s - m) * scale) goes to shared memory as the bf16 K-major
 //                   128B-swizzled A operand of the PV MMA.
 // Online softmax without touching O every block: the exponent reference m is only moved when the running row maximum
@@ -29,7 +30,7 @@ static constexpr int ATT_BM = 128;   // queries per tile (two tiles per CTA)
 static constexpr int ATT_BN = 128;   // keys per block
 static constexpr int ATT_D = 64;
 static constexpr int ATT_STAGES = 3;
-static constexpr int ATT_THREADS = 320;
+static constexpr int ATT_THREADS = 384;   // warpgroup 0: TMA + MMA (+2 idle warps), warpgroups 1/2: softmax of tile A/B
 static constexpr float ATT_RESCALE_THRESHOLD = 8.0f;   // log2 units
 
 struct AttnParams {
@@ -102,7 +103,9 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const uint32_t tmem_base = *tmem_ptr;
     // TMEM columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384)
 
-    if (warp == 0) {
+    if (warp < 4) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+      if (warp == 0) {
         if (lane == 0) {
             // ---------------- TMA producer ----------------
             mbar_expect_tx(q_full, (tileB_valid ? 2 : 1) * AttnSmem::Q_BYTES);
@@ -166,9 +169,11 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 kv_phase = nphase;
             }
         }
+      }
     } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
         // ---------------- softmax / output warps ----------------
-        const int x = (warp - 2) >> 2;                          // tile 0 (A) or 1 (B)
+        const int x = (warp - 4) >> 2;                          // tile 0 (A) or 1 (B)
         if (x == 0 || tileB_valid) {
             const int quad = warp & 3;
             const int row = quad * 32 + lane;                   // query row inside the tile
@@ -181,23 +186,28 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 mbar_wait(&s_full[x], j & 1);
                 tc_fence_after();
                 uint32_t s[128];
-                tmem_ld_32x32(tS + 0, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
-                tmem_ld_32x32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
-                tmem_ld_32x32(tS + 64, *reinterpret_cast<uint32_t(*)[32]>(&s[64]));
-                tmem_ld_32x32(tS + 96, *reinterpret_cast<uint32_t(*)[32]>(&s[96]));
+                tmem_ld_32x32_at<0>(tS + 0, s);
+                tmem_ld_32x32_at<32>(tS + 32, s);
+                tmem_ld_32x32_at<64>(tS + 64, s);
+                tmem_ld_32x32_at<96>(tS + 96, s);
                 tmem_ld_wait();
                 const int kv_valid = min(ATT_BN, p.Lk - j * ATT_BN);
-                float mx = -INFINITY;
-                if (kv_valid == ATT_BN) {
+                if (kv_valid != ATT_BN) {
 #pragma unroll
-                    for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 128; ++i) {
+                    for (int i = 0; i < 128; ++i)
                         if (i >= kv_valid) s[i] = 0xff800000u;   // -inf
-                        mx = fmaxf(mx, __uint_as_float(s[i]));
-                    }
                 }
+                // row maximum with 8 independent chains (a single chain would serialise 128 dependent FMNMX)
+                float mxa[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) mxa[t] = __uint_as_float(s[t]);
+#pragma unroll
+                for (int i = 8; i < 128; i += 8) {
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) mxa[t] = fmaxf(mxa[t], __uint_as_float(s[i + t]));
+                }
+                float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])),
+                                 fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
                 mx *= p.scale_log2;
                 // previous PV of this tile must have finished: it reads P (about to be overwritten) and updates O
                 if (j > 0) {
@@ -224,7 +234,9 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                         tmem_st_wait();
                     }
                 }
-                float lsum = 0.f;
+                float ls[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) ls[t] = 0.f;
 #pragma unroll
                 for (int c0 = 0; c0 < ATT_BN; c0 += 32) {
                     uint8_t* half_base = p_row + (c0 >> 6) * (AttnSmem::P_BYTES / 2);
@@ -234,7 +246,7 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
                         for (int t = 0; t < 8; ++t) {
                             e[t] = ex2_approx(fmaf(__uint_as_float(s[c0 + q * 8 + t]), p.scale_log2, -m_ref));
-                            lsum += e[t];
+                            ls[t] += e[t];
                         }
                         const int chunk = ((c0 & 63) >> 3) + q;         // 16-byte chunk index inside the 128-byte row
                         uint4 u;
@@ -245,7 +257,7 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                         *reinterpret_cast<uint4*>(half_base + ((chunk ^ (row & 7)) << 4)) = u;
                     }
                 }
-                l_run += lsum;
+                l_run += ((ls[0] + ls[1]) + (ls[2] + ls[3])) + ((ls[4] + ls[5]) + (ls[6] + ls[7]));
                 tc_fence_before();
                 fence_proxy_async_smem();   // generic-proxy writes of P -> visible to the tensor-core (async) proxy
                 __syncwarp();

@@ -191,6 +191,16 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
         : "r"(taddr)
         : "memory");
 }
+// same, into elements [BASE, BASE+32) of a larger register array (no address-taking, so the array stays in registers)
+template <int BASE, int N>
+__device__ __forceinline__ void tmem_ld_32x32_at(uint32_t taddr, uint32_t (&r)[N]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[BASE + 0]), "=r"(r[BASE + 1]), "=r"(r[BASE + 2]), "=r"(r[BASE + 3]), "=r"(r[BASE + 4]), "=r"(r[BASE + 5]), "=r"(r[BASE + 6]), "=r"(r[BASE + 7]), "=r"(r[BASE + 8]), "=r"(r[BASE + 9]), "=r"(r[BASE + 10]), "=r"(r[BASE + 11]), "=r"(r[BASE + 12]), "=r"(r[BASE + 13]), "=r"(r[BASE + 14]), "=r"(r[BASE + 15]), "=r"(r[BASE + 16]), "=r"(r[BASE + 17]), "=r"(r[BASE + 18]), "=r"(r[BASE + 19]), "=r"(r[BASE + 20]), "=r"(r[BASE + 21]), "=r"(r[BASE + 22]), "=r"(r[BASE + 23]), "=r"(r[BASE + 24]), "=r"(r[BASE + 25]), "=r"(r[BASE + 26]), "=r"(r[BASE + 27]), "=r"(r[BASE + 28]), "=r"(r[BASE + 29]), "=r"(r[BASE + 30]), "=r"(r[BASE + 31])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // registers -> TMEM: 32 lanes x 32 consecutive fp32 columns
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {

@@ -6,14 +6,15 @@
 // nn.Conv2d 1x1 (openaimodel.py:317, SUPIR_v0.py:48,87, model.py:124-126,164-175) and nn.Conv2d 3x3 stride 1 pad 1
 // (openaimodel.py:263,300-307; SUPIR_v0.py:79,82-83; model.py:108-117 ...).
 //
-// Design (one persistent CTA per SM, 192 threads, warp-specialised):
+// Design (one persistent CTA per SM, 320 threads, warp-specialised):
 //   warp 0 lane 0 : TMA producer.  A tile = 128 rows x 64 k (bf16, 128B-swizzled), W tile = BN rows x 64 k.
 //                   GEMM mode: A is a 2-D tensor map over [M, K].
 //                   CONV mode: A is a 4-D tensor map over the NHWC activation [B, H, W, C]; the tile's 128 rows are a
 //                   TH x TW pixel patch and the k-loop runs over (tap, 64-channel chunk); the tap shift is applied to the
 //                   TMA coordinates, and TMA's out-of-bounds zero fill IS the conv padding (no im2col buffer).
 //   warp 1 lane 0 : tcgen05.mma issuer (UMMA 128 x BN x 16, accumulators in TMEM, double-buffered across tiles).
-//   warps 2..5    : epilogue. tcgen05.ld 32 columns at a time; +bias, +per-batch vector (timestep embedding),
+//   warps 2..9    : epilogue, two warps per TMEM lane quadrant taking alternate 32-column chunks (tcgen05.ld of the next
+//                   chunk is in flight while the current one is converted and stored); +bias, +per-batch vector (timestep embedding),
 //                   SiLU / GEGLU, bf16 round, +residual, 64-byte-contiguous global stores.
 // Pipelines: smem full/empty ring (TMA <-> MMA) and TMEM full/empty (MMA <-> epilogue).
 #include "common.cuh"
@@ -25,7 +26,7 @@ namespace supir {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;
-static constexpr int GEMM_THREADS = 192;
+static constexpr int GEMM_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
 
 struct GemmKernelParams {
     int M, N, K;          // N = accumulator columns (before GEGLU halving)
@@ -55,7 +56,9 @@ struct GemmSmem {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 160 ? 5 : (BN == 128 ? 6 : 8));
+    static constexpr int ACC_STRIDE = (BN == 160) ? 256 : BN;          // TMEM column offset of the second accumulator
+    static constexpr int TMEM_COLS = (BN == 160) ? 512 : 2 * BN;       // allocation must be a power of two
     static constexpr int BAR_BYTES = 256;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
 };
@@ -90,12 +93,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
+            mbar_init(&tmem_empty[a], 8);  // one arrive per epilogue warp
         }
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_ptr, 2 * BN);
+        tmem_alloc(tmem_ptr, S::TMEM_COLS);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -148,7 +151,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
+                const uint32_t d_tmem = tmem_base + acc * S::ACC_STRIDE;
                 for (int kb = 0; kb < p.num_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
@@ -168,7 +171,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
+        // ===================== epilogue (warps 2..9) =====================
         const int quad = warp & 3;  // TMEM lane quadrant this warp may access
         const int row_in_tile = quad * 32 + lane;
         int acc = 0;
@@ -196,14 +199,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            const uint32_t t_row = tmem_base + acc * S::ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
+            const int half = (warp - 2) >> 2;          // this warp takes chunks half, half + 2, half + 4, ...
+            auto process = [&](uint32_t (&r)[32], int c0) {
                 const int n0 = nt * BN + c0;
-                if (n0 >= p.N) break;  // warp-uniform
-                uint32_t r[32];
-                tmem_ld_32x32(t_row + c0, r);
-                tmem_ld_wait();
                 if (row_ok) {
                     float v[32];
 #pragma unroll
@@ -306,6 +305,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         }
                     }
                 }
+            };
+            // software pipeline over this warp's chunks: the tcgen05.ld of the next chunk overlaps the stores of this one
+            constexpr int NCH = BN / 32;
+            uint32_t ra[32], rb[32];
+            int c = half;
+            if (c < NCH && nt * BN + c * 32 < p.N) tmem_ld_32x32(t_row + c * 32, ra);
+#pragma unroll 1
+            for (; c < NCH; c += 4) {
+                if (nt * BN + c * 32 >= p.N) break;                       // warp-uniform
+                tmem_ld_wait();
+                const int c2 = c + 2;
+                const bool has2 = c2 < NCH && nt * BN + c2 * 32 < p.N;
+                if (has2) tmem_ld_32x32(t_row + c2 * 32, rb);
+                process(ra, c * 32);
+                if (!has2) break;
+                tmem_ld_wait();
+                const int c4 = c + 4;
+                if (c4 < NCH && nt * BN + c4 * 32 < p.N) tmem_ld_32x32(t_row + c4 * 32, ra);
+                process(rb, c2 * 32);
             }
             tc_fence_before();
             __syncwarp();
@@ -318,7 +336,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 2 * BN);
+        tmem_dealloc(tmem_base, S::TMEM_COLS);
     }
 }
 
@@ -379,9 +397,9 @@ int device_sm_count() {
     return sms;
 }
 
-static int g_force_bn = 0;
-static long long g_desc_override = -1;   // debug: full 64-bit descriptor template (address bits zero), -1 = default
-static long long g_idesc_override = -1;  // debug: instruction descriptor, -1 = default
+extern int g_force_bn;
+extern long long g_desc_override;
+extern long long g_idesc_override;
 
 template <int BN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmKernelParams p, cudaStream_t st) {
@@ -407,30 +425,37 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmKerne
     return SUPIR_OK;
 }
 
-// choose the N tile: minimise (waves x per-tile cost); 256-wide tiles halve shared-memory traffic per flop.
-static int pick_bn(int m_tiles, int N, int force_bn) {
-    if (force_bn == 64 || force_bn == 128 || force_bn == 256) return force_bn;
+// choose the N tile: minimise (rounds over the SMs) x (per-tile time). 160 divides every channel count of SUPIR
+// (320..10240) exactly; 256 has the best shared-memory traffic per flop; narrow tiles fill the machine for small M.
+static int pick_bn(int m_tiles, int N, int num_kb, int force_bn) {
+    if (force_bn == 64 || force_bn == 128 || force_bn == 160 || force_bn == 256) return force_bn;
     const int sms = device_sm_count();
     int best = 128;
     double best_cost = 1e30;
-    const int cands[3] = {256, 128, 64};
-    for (int i = 0; i < 3; ++i) {
+    const int cands[4] = {256, 160, 128, 64};
+    for (int i = 0; i < 4; ++i) {
         const int bn = cands[i];
         if (bn > 64 && N <= bn / 2) continue;
         const long long tiles = (long long)m_tiles * ((N + bn - 1) / bn);
-        const long long waves = (tiles + sms - 1) / sms;
-        // per-tile cost model: MMA time ~ bn, plus a fixed prologue/epilogue overhead; narrow tiles are smem-bound
-        const double tile_cost = bn * (bn == 256 ? 1.0 : (bn == 128 ? 1.1 : 1.35)) + 24.0;
-        const double cost = waves * tile_cost;
+        const long long rounds = (tiles + sms - 1) / sms;
+        // MMA time of a tile ~ bn * num_kb (narrow tiles are shared-memory bound: 128-wide costs ~1.15x per column, 64-wide ~1.5x);
+        // plus a per-tile overhead (pipeline fill + epilogue not hidden on the last tile) of ~6 k-blocks of a 256-wide tile
+        const double per_col = bn == 256 ? 1.0 : (bn == 160 ? 1.2 : (bn == 128 ? 1.42 : 2.0));   // measured (profiles/r01_*perf2*)
+        const double tile_cost = bn * per_col * num_kb + 256.0 * 6.0;
+        const double cost = rounds * tile_cost;
         if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
     }
     return best;
 }
 
+int g_force_bn = 0;
+long long g_desc_override = -1;   // debug: full 64-bit descriptor template (address bits zero), -1 = default
+long long g_idesc_override = -1;  // debug: instruction descriptor, -1 = default
 
 static int run_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmKernelParams& p, cudaStream_t st) {
-    const int bn = pick_bn(p.num_m_tiles, p.N, g_force_bn);
+    const int bn = pick_bn(p.num_m_tiles, p.N, p.num_kb, g_force_bn);
     if (bn == 256) return launch_gemm<256>(tmA, tmB, p, st);
+    if (bn == 160) return launch_gemm<160>(tmA, tmB, p, st);
     if (bn == 128) return launch_gemm<128>(tmA, tmB, p, st);
     return launch_gemm<64>(tmA, tmB, p, st);
 }
@@ -488,7 +513,7 @@ extern "C" int supir_gemm_bf16(const void* A, long long lda, const void* W, long
     if (rc) return rc;
     SUPIR_REQUIRE(ldc >= p.n_out, "supir_gemm_bf16: ldc %lld < output columns %d", ldc, p.n_out);
     p.out = out; p.ldc = ldc;
-    const int bn = pick_bn(p.num_m_tiles, N, g_force_bn);
+    const int bn = pick_bn(p.num_m_tiles, N, p.num_kb, g_force_bn);
     CUtensorMap tmA, tmB;
     {
         const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
@@ -537,7 +562,7 @@ extern "C" int supir_conv3x3_bf16(const void* x, long long ldx, const void* Wp, 
     if (rc) return rc;
     SUPIR_REQUIRE(ldc >= p.n_out, "supir_conv3x3_bf16: ldc %lld < output columns %d", ldc, p.n_out);
     p.out = out; p.ldc = ldc;
-    const int bn = pick_bn(p.num_m_tiles, Cout, g_force_bn);
+    const int bn = pick_bn(p.num_m_tiles, Cout, p.num_kb, g_force_bn);
     CUtensorMap tmA, tmB;
     {
         const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Wd, (uint64_t)H, (uint64_t)B};

@@ -58,6 +58,21 @@ def shard_windows(num_windows, world_size, rank):
     return per, lo, hi
 
 
+def balanced_groups(n, max_group):
+    """Split n windows into ceil(n / max_group) contiguous groups whose sizes differ by at most one (at most two
+    distinct network batch sizes -> at most two captured CUDA graphs)."""
+    if n <= 0:
+        return []
+    k = (n + max_group - 1) // max_group
+    base, rem = divmod(n, k)
+    out, lo = [], 0
+    for i in range(k):
+        hi = lo + base + (1 if i < rem else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
 def exchange_window_outputs(tiles_out, rank, per):
     """The one collective of a tiled step: in-place all-gather of the per-rank blocks of `tiles_out`
     ([world*per, ...] fp32, rank r owns slots [r*per, (r+1)*per)). NCCL on GPUs, gloo in the CPU tests."""
@@ -173,7 +188,7 @@ class RestoreEDMSampler(BaseDiffusionSampler):
 
 
 class TiledRestoreEDMSampler(RestoreEDMSampler):
-    def __init__(self, tile_size=128, tile_stride=64, tile_batch=4, *args, **kwargs):
+    def __init__(self, tile_size=128, tile_stride=64, tile_batch=8, *args, **kwargs):
         super().__init__(*args, **kwargs)
         self.tile_size, self.tile_stride = tile_size, tile_stride
         self.tile_batch = max(1, int(tile_batch))        # windows stacked into one network call
@@ -258,8 +273,7 @@ class _TiledRun:
             if k["gamma"] > 0:
                 e_t = torch.empty_like(x_t)
                 ops.tile_gather(eps_noise, self.my_table, T, e_t)
-            for g0 in range(0, n_mine, smp.tile_batch):
-                g1 = min(g0 + smp.tile_batch, n_mine)
+            for g0, g1 in balanced_groups(n_mine, smp.tile_batch):
                 g = g1 - g0
 
                 def stack(key):

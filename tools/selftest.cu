@@ -436,7 +436,7 @@ int main(int argc, char** argv) {
     printf("device: %s sm_%d%d SMs=%d\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount);
     if (what == "bringup" || what == "all") bringup();
     if (what == "gemm" || what == "all") {
-        for (int bn : {64, 128, 256}) {
+        for (int bn : {64, 128, 160, 256}) {
             supir_set_gemm_tile_n(bn);
             test_gemm(128, 256, 64, 0, false, false, false, 0);
             test_gemm(128, 256, 256, 0, true, false, false, 0);
@@ -475,6 +475,22 @@ int main(int argc, char** argv) {
         perf_attention(2, 10, 16384, 16384);
         perf_attention(2, 10, 4096, 77);
         perf_attention(2, 20, 1024, 77);
+    }
+    if (what == "perf2" || what == "all") {
+        // shapes of the tiled workload at 8 windows per launch (B = 16): calibrates the tile-width cost model
+        struct Sh { int M, N, K, act; } shapes[] = {
+            {16384, 1280, 1280, 0}, {16384, 3840, 1280, 0}, {16384, 10240, 1280, 2}, {16384, 1280, 5120, 0},
+            {65536, 640, 640, 0}, {65536, 1920, 640, 0}, {65536, 5120, 640, 2}, {65536, 640, 2560, 0},
+            {2048, 1280, 1280, 0}, {2048, 3840, 1280, 0}, {8192, 640, 640, 0}, {1232, 163840, 2048, 0}};
+        for (auto& sh : shapes)
+            for (int bn : {0, 128, 160, 256}) perf_gemm(sh.M, sh.N, sh.K, sh.act, bn);
+        for (int bn : {0, 128, 160, 256}) {
+            perf_conv(16, 32, 32, 1280, 1280, bn);
+            perf_conv(16, 64, 64, 640, 640, bn);
+            perf_conv(16, 128, 128, 320, 320, bn);
+            perf_conv(16, 32, 32, 2560, 1280, bn);
+            perf_conv(16, 128, 128, 128, 1280, bn);
+        }
     }
     if (what == "perf" || what == "all") {
         for (int bn : {128, 256}) {
