@@ -222,7 +222,7 @@ def profile_dominant_kernel(net, device):
         e0.record()
         r = orig_gemm(a, w, out, **kw)
         e1.record()
-        rec.append((2.0 * a.shape[0] * w.shape[0] * a.shape[1], e0, e1))
+        rec.append((2.0 * a.shape[0] * w.shape[0] * a.shape[1], e0, e1, ("gemm", a.shape[0], w.shape[0], a.shape[1], kw.get("act", 0))))
         return r
 
     def conv(x, B, H, W, wp, out, **kw):
@@ -230,7 +230,7 @@ def profile_dominant_kernel(net, device):
         e0.record()
         r = orig_conv(x, B, H, W, wp, out, **kw)
         e1.record()
-        rec.append((2.0 * x.shape[0] * wp.shape[0] * wp.shape[1], e0, e1))
+        rec.append((2.0 * x.shape[0] * wp.shape[0] * wp.shape[1], e0, e1, ("conv3x3", x.shape[0], wp.shape[0], wp.shape[1], kw.get("act", 0))))
         return r
 
     B = 2 * 7      # the batch the 49-window step actually runs (7 groups of 7 windows, CFG pair)
@@ -251,6 +251,18 @@ def profile_dominant_kernel(net, device):
         ops.gemm, ops.conv3x3 = orig_gemm, orig_conv
     flops = sum(r[0] for r in rec)
     ms = sum(r[1].elapsed_time(r[2]) for r in rec)
+    dump = os.environ.get("SUPIR_BENCH_DUMP_SHAPES")
+    if dump:
+        agg = {}
+        for f, e0, e1, key in rec:
+            a = agg.setdefault(key, [0, 0.0, 0.0])
+            a[0] += 1
+            a[1] += e0.elapsed_time(e1)
+            a[2] += f
+        rows = sorted(({"op": k[0], "M": k[1], "N": k[2], "K": k[3], "act": k[4], "count": v[0], "ms": round(v[1], 3),
+                        "tflops": round(v[2] / (v[1] * 1e-3) / 1e12, 1)} for k, v in agg.items()), key=lambda r: -r["ms"])
+        with open(dump, "w") as f:
+            json.dump({"total_ms": ms, "total_tflop": flops / 1e12, "rows": rows, "order": [list(r[3]) for r in rec]}, f, indent=0)
     return flops, ms, len(rec)
 
 

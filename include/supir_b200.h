@@ -55,6 +55,8 @@ int supir_conv3x3_bf16(const void* x, long long ldx, const void* Wp, void* out, 
 
 /* debugging / tuning knob: force the N tile (64/128/256), 0 = heuristic */
 int supir_set_gemm_tile_n(int bn);
+/* debugging: 1 routes every GEMM through the direct-store epilogue instead of the shared-memory + TMA-store one */
+int supir_debug_force_direct_epilogue(int on);
 /* debugging: override the UMMA shared-memory descriptor template / instruction descriptor (-1 = built-in default) */
 int supir_debug_set_umma_descriptors(long long smem_desc_template, long long idesc);
 

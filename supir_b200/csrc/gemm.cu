@@ -31,6 +31,7 @@ static constexpr int GEMM_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9
 struct GemmKernelParams {
     int M, N, K;          // N = accumulator columns (before GEGLU halving)
     int num_m_tiles, num_n_tiles, num_kb;
+    int m_fastest;        // tile order: 1 = consecutive tiles share the W tile, 0 = they share the A tile
     // conv mode
     int conv;             // 0 gemm, 1 conv3x3
     int H, W, Cin, TH, TW, tiles_x, tiles_y, kchunks;
@@ -46,6 +47,8 @@ struct GemmKernelParams {
     long long ldc;
     int out_f32;
     int n_out;            // valid output columns (N or N/2 for GEGLU)
+    int staged;           // 1: epilogue through shared memory (bias tile in smem, TMA-loaded residual, TMA store)
+    int has_res;          // staged path: residual tensor map valid
     uint32_t desc_hi;     // upper 32 bits of the shared-memory matrix descriptor (SBO / version / swizzle mode)
     uint32_t desc_lbo;    // LBO field (bits 16..29 of the low word), pre-shifted
     uint32_t idesc;       // tcgen05 instruction descriptor
@@ -56,16 +59,21 @@ struct GemmSmem {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 160 ? 5 : (BN == 128 ? 6 : 8));
+    static constexpr int STAGES = (BN == 256) ? 3 : (BN == 160 ? 4 : (BN == 128 ? 4 : 6));
+    // epilogue staging: per half-group (4 warps = 128 rows) two 8 KB output buffers and two 8 KB residual buffers
+    // (128 rows x 32 bf16 columns, 64B-swizzled), plus the tile's bias (+ per-image vector) for both accumulators
+    static constexpr int CH_BYTES = BM * 32 * 2;
+    static constexpr int EPI_BYTES = 8 * CH_BYTES + 2 * BN * 4;
     static constexpr int ACC_STRIDE = (BN == 160) ? 256 : BN;          // TMEM column offset of the second accumulator
     static constexpr int TMEM_COLS = (BN == 160) ? 512 : 2 * BN;       // allocation must be a power of two
     static constexpr int BAR_BYTES = 256;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
 };
 
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                     const GemmKernelParams p) {
     using S = GemmSmem<BN>;
     constexpr int STAGES = S::STAGES;
@@ -73,12 +81,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * S::A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+    uint8_t* smem_epi = smem + STAGES * S::STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + S::EPI_BYTES);
     uint64_t* full_bar = bars;                    // [STAGES]
     uint64_t* empty_bar = bars + STAGES;          // [STAGES]
     uint64_t* tmem_full = bars + 2 * STAGES;      // [2]
     uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint64_t* res_full = bars + 2 * STAGES + 4;   // [2 half-groups][2 buffers]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -94,6 +104,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
             mbar_init(&tmem_empty[a], 8);  // one arrive per epilogue warp
+        }
+        for (int a = 0; a < 4; ++a) mbar_init(&res_full[a], 1);
+        if (p.staged) {
+            tma_prefetch_desc(&tmC);
+            if (p.has_res) tma_prefetch_desc(&tmR);
         }
         fence_barrier_init();
     }
@@ -112,8 +127,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int mt = tile % p.num_m_tiles;
-                const int nt = tile / p.num_m_tiles;
+                const int mt = p.m_fastest ? tile % p.num_m_tiles : tile / p.num_n_tiles;
+                const int nt = p.m_fastest ? tile / p.num_m_tiles : tile % p.num_n_tiles;
                 int b = 0, y0 = 0, x0 = 0;
                 if (p.conv) {
                     const int per_img = p.tiles_x * p.tiles_y;
@@ -170,15 +185,167 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
+    } else if (p.staged) {
+        // ===================== epilogue, staged through shared memory (warps 2..9) =====================
+        // half-group h = 4 warps = all 128 accumulator rows; it owns the 32-column chunks c = h, h+2, ... of the tile.
+        // Per chunk: TMEM -> registers (+bias, activation, +residual read from a TMA-loaded smem tile) -> bf16 -> swizzled
+        // smem -> one TMA store. Global traffic is whole lines moved by the TMA engine; the LSU only sees shared memory.
+        const int quad = warp & 3;
+        const int h = (warp - 2) >> 2;
+        const int row = quad * 32 + lane;                          // accumulator row = TMEM lane
+        const bool elected = (warp == 2 + 4 * h) && lane == 0;
+        const int epi_tid = (warp - 2) * 32 + lane;                // 0..255
+        const bool geglu = p.act == 2;
+        uint8_t* stage_c = smem_epi + h * 2 * S::CH_BYTES;
+        uint8_t* stage_r = smem_epi + 4 * S::CH_BYTES + h * 2 * S::CH_BYTES;
+        float* s_bias = reinterpret_cast<float*>(smem_epi + 8 * S::CH_BYTES);
+        uint64_t* my_res_full = res_full + 2 * h;
+        // swizzled 16-byte chunk position inside a staging row (64B swizzle for 64-byte rows, 32B swizzle for GEGLU's 32-byte rows)
+        const int row_bytes = geglu ? 32 : 64;
+        const int sw = geglu ? ((row >> 2) & 1) : ((row >> 1) & 3);
+        uint32_t cnt = 0;                                          // chunks processed by this half-group (buffer parity)
+        uint32_t res_phase[2] = {0, 0};
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        constexpr int NCH = BN / 32;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int mt = p.m_fastest ? tile % p.num_m_tiles : tile / p.num_n_tiles;
+            const int nt = p.m_fastest ? tile / p.num_m_tiles : tile % p.num_n_tiles;
+            int cb = 0, cy0 = 0, cx0 = 0;
+            if (p.conv) {
+                const int per_img = p.tiles_x * p.tiles_y;
+                cb = mt / per_img;
+                const int r = mt % per_img;
+                cy0 = (r / p.tiles_x) * p.TH;
+                cx0 = (r % p.tiles_x) * p.TW;
+            }
+            // number of chunks of this tile that hold valid columns, and how many of them are mine
+            int nvalid = (p.N - nt * BN + 31) / 32;
+            nvalid = nvalid > NCH ? NCH : nvalid;
+            const int nck = nvalid > h ? (nvalid - h + 1) / 2 : 0;
+            auto out_col = [&](int k) { const int n0 = nt * BN + (h + 2 * k) * 32; return geglu ? (n0 >> 1) : n0; };
+            auto issue_res = [&](int k, int buf) {
+                mbar_expect_tx(&my_res_full[buf], BM * 64);
+                if (p.conv) tma_load_4d(stage_r + buf * S::CH_BYTES, &tmR, &my_res_full[buf], out_col(k), cx0, cy0, cb);
+                else tma_load_2d(stage_r + buf * S::CH_BYTES, &tmR, &my_res_full[buf], out_col(k), mt * BM);
+            };
+            // tile prologue: bias (+ per-image vector) for the tile's columns; first two residual chunks
+            float* sb = s_bias + acc * BN;
+            if (epi_tid < BN) {
+                const int n = nt * BN + epi_tid;
+                float b = 0.f;
+                if (n < p.N) {
+                    if (p.bias) b = __ldg(p.bias + n);
+                    if (p.rowvec) b += __ldg(p.rowvec + (long long)cb * p.rowvec_ld + n);
+                }
+                sb[epi_tid] = b;
+            }
+            named_bar_sync(5, 256);
+            if (p.has_res && elected) {
+                if (nck > 0) issue_res(0, cnt & 1);
+                if (nck > 1) issue_res(1, (cnt + 1) & 1);
+            }
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + acc * S::ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
+            uint32_t ra[32], rb[32];
+            if (nck > 0) tmem_ld_32x32(t_row + h * 32, ra);
+            auto finish = [&](uint32_t (&r)[32], int k) {
+                const int c = h + 2 * k;
+                const int buf = (cnt + k) & 1;
+                const float* bc = sb + c * 32;
+                uint4 q[4];
+                if (geglu) {
+                    float o[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float xv = bf16_round(__uint_as_float(r[j]) + bc[j]);
+                        const float gv = bf16_round(__uint_as_float(r[16 + j]) + bc[16 + j]);
+                        o[j] = xv * bf16_round(gelu_erf_f(gv));
+                    }
+                    q[0] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+                    q[1] = make_uint4(pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]), pack_bf16x2(o[12], o[13]), pack_bf16x2(o[14], o[15]));
+                } else {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(bc + j);
+                        v[j] = __uint_as_float(r[j]) + b4.x;
+                        v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+                        v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
+                        v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+                    }
+                    if (p.act == 1) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = silu_f(bf16_round(v[j]));
+                    }
+                    if (p.has_res) {
+                        mbar_wait(&my_res_full[buf], res_phase[buf]);
+                        res_phase[buf] ^= 1;
+                        const uint8_t* rrow = stage_r + buf * S::CH_BYTES + row * 64;
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const uint4 u = *reinterpret_cast<const uint4*>(rrow + ((j4 ^ sw) << 4));
+                            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const float2 f = unpack_bf16x2(w[t]);
+                                v[j4 * 8 + 2 * t] = bf16_round(v[j4 * 8 + 2 * t]) + f.x;
+                                v[j4 * 8 + 2 * t + 1] = bf16_round(v[j4 * 8 + 2 * t + 1]) + f.y;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4)
+                        q[j4] = make_uint4(pack_bf16x2(v[j4 * 8], v[j4 * 8 + 1]), pack_bf16x2(v[j4 * 8 + 2], v[j4 * 8 + 3]),
+                                           pack_bf16x2(v[j4 * 8 + 4], v[j4 * 8 + 5]), pack_bf16x2(v[j4 * 8 + 6], v[j4 * 8 + 7]));
+                }
+                // the TMA store issued two chunks ago read this staging buffer: make sure it is done, tell the group
+                if (elected) bulk_wait_group_read<1>();
+                named_bar_sync(1 + h, 128);
+                uint8_t* crow = stage_c + buf * S::CH_BYTES + row * row_bytes;
+                if (geglu) {
+                    *reinterpret_cast<uint4*>(crow + ((0 ^ sw) << 4)) = q[0];
+                    *reinterpret_cast<uint4*>(crow + ((1 ^ sw) << 4)) = q[1];
+                } else {
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) *reinterpret_cast<uint4*>(crow + ((j4 ^ sw) << 4)) = q[j4];
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(1 + h, 128);
+                if (elected) {
+                    if (p.conv) tma_store_4d(&tmC, stage_c + buf * S::CH_BYTES, out_col(k), cx0, cy0, cb);
+                    else tma_store_2d(&tmC, stage_c + buf * S::CH_BYTES, out_col(k), mt * BM);
+                    bulk_commit_group();
+                    if (p.has_res && k + 2 < nck) issue_res(k + 2, buf);
+                }
+            };
+#pragma unroll 1
+            for (int k = 0; k < nck; k += 2) {
+                tmem_ld_wait();
+                if (k + 1 < nck) tmem_ld_32x32(t_row + (h + 2 * (k + 1)) * 32, rb);
+                else { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&tmem_empty[acc]); }
+                finish(ra, k);
+                if (k + 1 >= nck) break;
+                tmem_ld_wait();
+                if (k + 2 < nck) tmem_ld_32x32(t_row + (h + 2 * (k + 2)) * 32, ra);
+                else { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&tmem_empty[acc]); }
+                finish(rb, k + 1);
+            }
+            if (nck == 0) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&tmem_empty[acc]); }
+            cnt += nck;
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (elected) bulk_wait_group_read<0>();      // shared memory must outlive the last TMA stores
     } else {
-        // ===================== epilogue (warps 2..9) =====================
+        // ===================== epilogue, direct global stores (fp32 output / unaligned cases; warps 2..9) =================
         const int quad = warp & 3;  // TMEM lane quadrant this warp may access
         const int row_in_tile = quad * 32 + lane;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int mt = tile % p.num_m_tiles;
-            const int nt = tile / p.num_m_tiles;
+            const int mt = p.m_fastest ? tile % p.num_m_tiles : tile / p.num_n_tiles;
+            const int nt = p.m_fastest ? tile / p.num_m_tiles : tile % p.num_n_tiles;
             // global row / validity
             long long grow;
             int batch_idx;
@@ -362,8 +529,8 @@ static PFN_tmapEncodeTiled get_encode_fn() {
 }
 
 // rank-N bf16 tensor map with 128B swizzle; dims/strides innermost first; strides in ELEMENTS for dims 1..rank-1
-int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
-                   const uint32_t* box) {
+int make_tmap_bf16_sw(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                      const uint32_t* box, int swizzle_bytes) {
     PFN_tmapEncodeTiled fn = get_encode_fn();
     if (!fn) return set_error(SUPIR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t gdim[5], gstr[4];
@@ -379,11 +546,18 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* d
     for (int i = 0; i + 1 < rank; ++i)
         if (gstr[i] % 16 != 0) return set_error(SUPIR_ERR_INVALID, "TMA stride %d (%llu B) not a multiple of 16", i,
                                                  (unsigned long long)gstr[i]);
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                  : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(SUPIR_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return SUPIR_OK;
+}
+
+int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                   const uint32_t* box) {
+    return make_tmap_bf16_sw(m, base, rank, dims, strides_elems, box, 128);
 }
 
 int device_sm_count() {
@@ -402,7 +576,8 @@ extern long long g_desc_override;
 extern long long g_idesc_override;
 
 template <int BN>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmKernelParams p, cudaStream_t st) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
+                       GemmKernelParams p, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         SUPIR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -418,8 +593,19 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmKerne
         p.idesc = g_idesc_override >= 0 ? (uint32_t)g_idesc_override : umma_idesc_bf16(BM, BN);
     }
     const int tiles = p.num_m_tiles * p.num_n_tiles;
+    {
+        // tile order that minimises HBM traffic under a simple L2 model: the CTAs running together (one round) either share
+        // a W tile (m-fastest; A is re-streamed once per n-tile unless it fits L2) or share an A tile (n-fastest; W is
+        // re-streamed once per round of m-tiles unless it fits L2)
+        const double l2 = 64e6;
+        const double a_bytes = 2.0 * p.M * (p.conv ? p.Cin : p.K), w_bytes = 2.0 * p.N * p.K;
+        const double rounds_m = (double)p.num_m_tiles * p.num_n_tiles / device_sm_count();
+        const double t_mfast = w_bytes + (a_bytes <= l2 ? a_bytes : a_bytes * p.num_n_tiles);
+        const double t_nfast = a_bytes + (w_bytes <= l2 ? w_bytes : w_bytes * (rounds_m < 1 ? 1 : rounds_m));
+        p.m_fastest = t_mfast < t_nfast ? 1 : 0;
+    }
     const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-    gemm_tcgen05_kernel<BN><<<grid, GEMM_THREADS, GemmSmem<BN>::TOTAL, st>>>(tmA, tmB, p);
+    gemm_tcgen05_kernel<BN><<<grid, GEMM_THREADS, GemmSmem<BN>::TOTAL, st>>>(tmA, tmB, tmC, tmR, p);
     count_launch();
     SUPIR_CHECK_CUDA(cudaGetLastError());
     return SUPIR_OK;
@@ -452,12 +638,58 @@ int g_force_bn = 0;
 long long g_desc_override = -1;   // debug: full 64-bit descriptor template (address bits zero), -1 = default
 long long g_idesc_override = -1;  // debug: instruction descriptor, -1 = default
 
+int g_force_direct_epilogue = 0;   // debug: 1 disables the staged (smem + TMA store) epilogue
+
+// staged epilogue applies to bf16 outputs with 16-byte aligned rows; it needs the per-image vector to be uniform per tile
+static bool can_stage(const GemmKernelParams& p) {
+    if (g_force_direct_epilogue || p.out_f32) return false;
+    if ((p.ldc & 7) || (reinterpret_cast<uintptr_t>(p.out) & 15)) return false;
+    if (p.n_out < (p.act == 2 ? 16 : 32)) return false;
+    if (p.rowvec && !p.conv) return false;
+    if (p.residual && (p.act == 2 || (p.ldr & 7) || (reinterpret_cast<uintptr_t>(p.residual) & 15))) return false;
+    return true;
+}
+
+// output / residual tensor maps of the staged epilogue: 32-column (GEGLU: 16-column) chunks of the tile's 128 rows
+static int make_epi_maps(const GemmKernelParams& p, CUtensorMap* tmC, CUtensorMap* tmR) {
+    const uint32_t cols = p.act == 2 ? 16 : 32;
+    const int sw = p.act == 2 ? 32 : 64;
+    int rc;
+    if (p.conv) {
+        const uint64_t dims[4] = {(uint64_t)p.n_out, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)(p.M / ((long long)p.H * p.W))};
+        const uint32_t box[4] = {cols, (uint32_t)p.TW, (uint32_t)p.TH, 1};
+        const uint64_t sc[3] = {(uint64_t)p.ldc, (uint64_t)p.ldc * p.W, (uint64_t)p.ldc * p.W * p.H};
+        if ((rc = make_tmap_bf16_sw(tmC, p.out, 4, dims, sc, box, sw))) return rc;
+        if (p.residual) {
+            const uint64_t sr[3] = {(uint64_t)p.ldr, (uint64_t)p.ldr * p.W, (uint64_t)p.ldr * p.W * p.H};
+            if ((rc = make_tmap_bf16_sw(tmR, p.residual, 4, dims, sr, box, sw))) return rc;
+        }
+    } else {
+        const uint64_t dims[2] = {(uint64_t)p.n_out, (uint64_t)p.M};
+        const uint32_t box[2] = {cols, (uint32_t)BM};
+        const uint64_t sc[1] = {(uint64_t)p.ldc};
+        if ((rc = make_tmap_bf16_sw(tmC, p.out, 2, dims, sc, box, sw))) return rc;
+        if (p.residual) {
+            const uint64_t sr[1] = {(uint64_t)p.ldr};
+            if ((rc = make_tmap_bf16_sw(tmR, p.residual, 2, dims, sr, box, sw))) return rc;
+        }
+    }
+    return SUPIR_OK;
+}
+
 static int run_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmKernelParams& p, cudaStream_t st) {
+    CUtensorMap tmC = tmA, tmR = tmA;   // placeholders when the direct epilogue is used
+    p.staged = can_stage(p) ? 1 : 0;
+    p.has_res = (p.staged && p.residual) ? 1 : 0;
+    if (p.staged) {
+        const int rc = make_epi_maps(p, &tmC, &tmR);
+        if (rc) return rc;
+    }
     const int bn = pick_bn(p.num_m_tiles, p.N, p.num_kb, g_force_bn);
-    if (bn == 256) return launch_gemm<256>(tmA, tmB, p, st);
-    if (bn == 160) return launch_gemm<160>(tmA, tmB, p, st);
-    if (bn == 128) return launch_gemm<128>(tmA, tmB, p, st);
-    return launch_gemm<64>(tmA, tmB, p, st);
+    if (bn == 256) return launch_gemm<256>(tmA, tmB, tmC, tmR, p, st);
+    if (bn == 160) return launch_gemm<160>(tmA, tmB, tmC, tmR, p, st);
+    if (bn == 128) return launch_gemm<128>(tmA, tmB, tmC, tmR, p, st);
+    return launch_gemm<64>(tmA, tmB, tmC, tmR, p, st);
 }
 
 static int fill_epilogue(GemmKernelParams& p, const supir_epilogue* ep, int N) {
@@ -490,6 +722,11 @@ using namespace supir;
 extern "C" int supir_debug_set_umma_descriptors(long long smem_desc_template, long long idesc) {
     g_desc_override = smem_desc_template;
     g_idesc_override = idesc;
+    return SUPIR_OK;
+}
+
+extern "C" int supir_debug_force_direct_epilogue(int on) {
+    g_force_direct_epilogue = on;
     return SUPIR_OK;
 }
 

@@ -404,6 +404,52 @@ static void perf_attention(int B, int H, int Lq, int Lk) {
     fflush(stdout);
 }
 
+
+// data / bias / duration sensitivity of the GEMM (power cap, epilogue cost): constant vs random operands, with/without bias+residual
+static void perf_gemm_variants(int M, int N, int K, int act) {
+    const int n_out = act == 2 ? N / 2 : N;
+    Rng rng(5);
+    std::vector<float> hA((size_t)M * K), hW((size_t)N * K), hb(N);
+    for (auto& v : hA) v = rng.normal();
+    for (auto& v : hW) v = rng.normal(1.0f / sqrtf((float)K));
+    for (auto& v : hb) v = rng.normal(0.3f);
+    auto Ab = to_bf16(hA), Wb = to_bf16(hW);
+    __nv_bfloat16 *dA = dev_copy(Ab), *dW = dev_copy(Wb), *dOut, *dRes, *cA, *cW;
+    float* dB = dev_copy(hb);
+    CK(cudaMalloc(&dOut, (size_t)M * n_out * 2));
+    CK(cudaMalloc(&dRes, (size_t)M * n_out * 2));
+    CK(cudaMemset(dRes, 0x3c, (size_t)M * n_out * 2));
+    CK(cudaMalloc(&cA, (size_t)M * K * 2));
+    CK(cudaMalloc(&cW, (size_t)N * K * 2));
+    CK(cudaMemset(cA, 0x11, (size_t)M * K * 2));
+    CK(cudaMemset(cW, 0x11, (size_t)N * K * 2));
+    struct V { const char* name; bool rnd, bias, res; int iters; } vs[] = {
+        {"const data, no bias", false, false, false, 20}, {"random data, no bias", true, false, false, 20},
+        {"random data, bias", true, true, false, 20},     {"random data, bias+res", true, true, true, 20},
+        {"random data, bias, 300 iters", true, true, false, 300}};
+    for (auto& v : vs) {
+        supir_epilogue ep{};
+        ep.act = act;
+        ep.bias = v.bias ? dB : nullptr;
+        ep.residual = v.res ? dRes : nullptr;
+        ep.ldr = n_out;
+        const __nv_bfloat16 *a = v.rnd ? dA : cA, *w = v.rnd ? dW : cW;
+        for (int i = 0; i < 3; ++i) supir_gemm_bf16(a, K, w, K, dOut, n_out, M, N, K, &ep, nullptr);
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0);
+        for (int i = 0; i < v.iters; ++i) supir_gemm_bf16(a, K, w, K, dOut, n_out, M, N, K, &ep, nullptr);
+        cudaEventRecord(e1);
+        CK(cudaEventSynchronize(e1));
+        float ms;
+        cudaEventElapsedTime(&ms, e0, e1);
+        ms /= v.iters;
+        printf("[PERF3] gemm M=%d N=%d K=%d act=%d %-32s: %.3f ms  %.1f TFLOP/s\n", M, N, K, act, v.name, ms, 2.0 * M * N * K / ms / 1e9);
+        fflush(stdout);
+    }
+    cudaFree(dA); cudaFree(dW); cudaFree(dOut); cudaFree(dRes); cudaFree(cA); cudaFree(cW); cudaFree(dB);
+}
+
 // descriptor bring-up: try the default, then a few alternates, on a tiny identity GEMM
 static void bringup() {
     printf("== bring-up: identity GEMM 128x64x64 with default descriptors\n");
@@ -475,6 +521,13 @@ int main(int argc, char** argv) {
         perf_attention(2, 10, 16384, 16384);
         perf_attention(2, 10, 4096, 77);
         perf_attention(2, 20, 1024, 77);
+    }
+    if (what == "perf3" || what == "all") {
+        perf_gemm_variants(14336, 10240, 1280, 2);
+        perf_gemm_variants(14336, 1280, 1280, 0);
+        perf_gemm_variants(57344, 640, 640, 0);
+        perf_gemm_variants(57344, 5120, 640, 2);
+        perf_gemm_variants(8192, 8192, 8192, 0);
     }
     if (what == "perf2" || what == "all") {
         // shapes of the tiled workload at 8 windows per launch (B = 16): calibrates the tile-width cost model
