@@ -138,23 +138,33 @@ def time_oracle_window(sd, side, repeats):
     return times
 
 
-def mp_per_s_from_window_time(sec_per_window_step, side):
-    """Extrapolate a measured window-step time to the whole job: 49 windows x 50 steps, scaled by the FLOP ratio to the
-    128-latent window the job uses (the VAE is ~1.4 % of the job's work and is left out: this flatters the CPU)."""
-    sec_128 = sec_per_window_step * FLOP_WINDOW / flop_denoiser(side)
+def mp_per_s_from_window_time(sec_128):
+    """Whole-job throughput from the time of one 128-latent window step: 49 windows x 50 steps (the VAE, ~1.4 % of the
+    job's work, is left out: this flatters the CPU)."""
     return MEGAPIXELS / (sec_128 * 49 * EDM_STEPS), sec_128 * 49 * 1e3
 
 
-def pick_side(budget_s, sd):
-    """Largest window (latent side) whose oracle call fits the per-step budget, found by probing upwards."""
-    side, last = 16, None
-    time_oracle_window(sd, 16, 1)        # warm-up: first touch of the 15.5 GB of weights, oneDNN primitive creation
+def probe_oracle(budget_s, sd, repeats=1):
+    """Time the oracle's denoiser call on growing windows (latent side 16, 32, 64, 128) while a call fits the budget.
+    Returns ({side: seconds}, estimated seconds for the 128-latent window). When 128 itself was not reached the estimate
+    is a two-point fit t = a + b * FLOP(side) through the two largest measured sizes (a = the size-independent cost of
+    streaming 15.5 GB of fp32 weights), which is fairer to the CPU than scaling a tiny window by FLOPs alone."""
+    time_oracle_window(sd, 16, 1)        # warm-up: first touch of the weights, oneDNN primitive creation
+    meas, side = {}, 16
     while True:
-        t = min(time_oracle_window(sd, side, 1))
-        last = (side, t)
-        if side >= 128 or t * 4.5 > budget_s:
-            return last
+        meas[side] = float(np.mean(time_oracle_window(sd, side, repeats)))
+        if side >= 128 or meas[side] * 4.5 > budget_s:
+            break
         side *= 2
+    sides = sorted(meas)
+    if 128 in meas:
+        return meas, meas[128]
+    if len(sides) == 1:
+        return meas, meas[sides[0]] * FLOP_WINDOW / flop_denoiser(sides[0])
+    s0, s1 = sides[-2], sides[-1]
+    b = (meas[s1] - meas[s0]) / (flop_denoiser(s1) - flop_denoiser(s0))
+    a = max(meas[s1] - b * flop_denoiser(s1), 0.0)
+    return meas, a + max(b, 0.0) * FLOP_WINDOW
 
 
 def run_reference(args):
@@ -165,13 +175,14 @@ def run_reference(args):
     torch.set_num_threads(cores)
     sd = oracle_state_dict()
     total_budget = float(os.environ.get("SUPIR_BENCH_REF_BUDGET_S", "150"))
-    side, _ = pick_side(total_budget / max(args.steps + args.warmup, 1), sd)
-    time_oracle_window(sd, side, args.warmup) if args.warmup > 0 else None
-    times = time_oracle_window(sd, side, args.steps)
-    sec = float(np.mean(times))
-    mps, ms_step = mp_per_s_from_window_time(sec, side)
-    sample = (f"{args.steps} timed oracle calls (fp32 torch restatement of the reference, {cores} threads) of control+UNet on ONE "
-              f"{side}x{side}-latent window (CFG pair); scaled by FLOPs to the 128-latent window, x49 windows x50 steps; VAE omitted")
+    reps = max(args.steps, 1)
+    meas, sec_128 = probe_oracle(total_budget / max(args.steps + args.warmup, 1), sd, repeats=reps)
+    side = max(meas)
+    sec = meas[side]
+    mps, ms_step = mp_per_s_from_window_time(sec_128)
+    sample = (f"{reps} timed oracle calls per size (fp32 torch restatement of the reference, {cores} threads) of control+UNet on ONE "
+              f"window (CFG pair) at latent sides {sorted(meas)}: {[round(meas[k], 2) for k in sorted(meas)]} s; 128-latent window "
+              f"estimated {sec_128:.1f} s (measured if 128 is listed, else two-point fit a + b*FLOP); x49 windows x50 steps; VAE omitted")
     print(json.dumps({
         "impl": "reference", "metric": "megapixels_per_sec", "value": mps, "unit": "MP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
@@ -387,12 +398,12 @@ def run_supir(args):
         cores = min(os.cpu_count() or 1, int(os.environ.get("SUPIR_BENCH_CPU_THREADS", "64")))
         torch.set_num_threads(cores)
         sd = oracle_state_dict()
-        side, _ = pick_side(float(os.environ.get("SUPIR_BENCH_CPU_BUDGET_S", "25")), sd)
-        sec = min(time_oracle_window(sd, side, 1))
-        mps, _ = mp_per_s_from_window_time(sec, side)
+        meas, sec_128 = probe_oracle(float(os.environ.get("SUPIR_BENCH_CPU_BUDGET_S", "25")), sd)
+        mps, _ = mp_per_s_from_window_time(sec_128)
         cpu = {"value": mps, "unit": "MP/s", "cores": cores, "kind": "port",
-               "sample": f"1 oracle call (fp32, {cores} threads) of control+UNet on one {side}x{side}-latent window (CFG pair), {sec:.2f} s; "
-                         f"scaled by FLOPs to the 128-latent window x49 windows x50 steps; VAE omitted"}
+               "sample": f"oracle calls (fp32, {cores} threads) of control+UNet on one window (CFG pair) at latent sides {sorted(meas)}: "
+                         f"{[round(meas[k], 2) for k in sorted(meas)]} s; 128-latent window estimated {sec_128:.1f} s "
+                         f"(two-point fit a + b*FLOP unless 128 was measured); x49 windows x50 steps; VAE omitted"}
     line = {
         "metric": "megapixels_per_sec", "value": MEGAPIXELS / total_s, "unit": "MP/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
