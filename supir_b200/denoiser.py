@@ -30,7 +30,7 @@ class EpsScaling:
 class LegacyDDPMDiscretization:
     def __init__(self, linear_start=0.00085, linear_end=0.0120, num_timesteps=1000):
         self.num_timesteps = num_timesteps
-        betas = torch.linspace(linear_start ** 0.5, linear_end ** 0.5, num_timesteps, dtype=torch.float64) ** 2
+        betas = torch.linspace(linear_start ** 0.5, linear_end ** 0.5, num_timesteps, dtype=torch.float64, device="cpu") ** 2
         self.alphas_cumprod = np.cumprod(1.0 - betas.numpy(), axis=0)
 
     def get_sigmas(self, n, device="cpu"):

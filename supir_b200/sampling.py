@@ -192,6 +192,7 @@ class TiledRestoreEDMSampler(RestoreEDMSampler):
         super().__init__(*args, **kwargs)
         self.tile_size, self.tile_stride = tile_size, tile_stride
         self.tile_batch = max(1, int(tile_batch))        # windows stacked into one network call
+        self.shard = True                                # shard windows over torch.distributed ranks when initialised
         self._weights = None
 
     @property
@@ -237,7 +238,7 @@ class _TiledRun:
         lq = lq.contiguous().float()
         xc = x_center.contiguous().float()
         self.world, self.rank = ((dist.get_world_size(), dist.get_rank())
-                                 if dist.is_available() and dist.is_initialized() else (1, 0))
+                                 if smp.shard and dist.is_available() and dist.is_initialized() else (1, 0))
         self.per, self.lo, self.hi = shard_windows(nw, self.world, self.rank)
         slots = self.per * self.world
         table = torch.full((slots, 4), -1, dtype=torch.int32)

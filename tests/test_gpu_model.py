@@ -1,0 +1,112 @@
+"""End-to-end GPU test of the engine (supir_b200.model.SUPIRModel.batchify_sample: stage-1 encode/decode, re-encode with the
+CPU-generator posterior sample, untiled RestoreEDMSampler with the fused step kernels, final decode) against the same
+pipeline composed from the CPU oracle with identical weights, inputs and noise. Also the full-depth SDXL configuration of
+the control + UNet pair against the oracle (BASELINE configs[0] shape family)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from weights import make_state_dict, randn
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+DISC = {"target": "sgm.modules.diffusionmodules.discretizer.LegacyDDPMDiscretization"}
+
+
+class SeededNoise:
+    def __init__(self, base):
+        self.base, self.n = base, 0
+
+    def __call__(self, x, **k):
+        self.n += 1
+        return randn(tuple(x.shape), self.base + self.n).to(x.device, x.dtype)
+
+
+def rel_fro(a, b):
+    return float((a - b).norm() / b.norm())
+
+
+def test_engine_batchify_sample_vs_oracle_pipeline(monkeypatch):
+    from oracle import sampler as osamp, unet as ounet, vae as ovae
+    from supir_b200 import model as smodel
+    gu = np.load(os.path.join(G, "unet_fullwidth_depth1.npz"))
+    gv = np.load(os.path.join(G, "vae_tiny.npz"))
+    ucfg, vcfg = json.loads(str(gu["cfg"])), json.loads(str(gv["cfg"]))
+    sd_net = make_state_dict(json.loads(str(gu["shapes"])), seed=31)
+    sd_vae = make_state_dict(json.loads(str(gv["shapes"])), seed=71)
+    sd_vae.update({"denoise_encoder." + k[len("encoder."):]: v for k, v in sd_vae.items() if k.startswith("encoder.")})
+    cfg = dict(
+        control_stage_config={"target": "SUPIR.modules.SUPIR_v0.GLVControl", "params": dict(ucfg, input_upscale=1)},
+        network_config={"target": "SUPIR.modules.SUPIR_v0.LightGLVUNet",
+                        "params": dict(ucfg, mode="XL-base", project_type="ZeroSFT", project_channel_scale=2)},
+        network_wrapper="sgm.modules.diffusionmodules.wrappers.ControlWrapper",
+        denoiser_config={"target": "sgm.modules.diffusionmodules.denoiser.DiscreteDenoiserWithControl",
+                         "params": {"num_idx": 1000, "weighting_config": {"target": "sgm.modules.diffusionmodules.denoiser_weighting.EpsWeighting"},
+                                    "scaling_config": {"target": "sgm.modules.diffusionmodules.denoiser_scaling.EpsScaling"},
+                                    "discretization_config": DISC}},
+        first_stage_config={"target": "sgm.models.autoencoder.AutoencoderKLInferenceWrapper",
+                            "params": {"embed_dim": 4, "ddconfig": vcfg, "lossconfig": {"target": "torch.nn.Identity"}}},
+        sampler_config={"target": "sgm.modules.diffusionmodules.sampling.RestoreEDMSampler",
+                        "params": {"num_steps": 100, "restore_cfg": 4.0, "s_churn": 0, "s_noise": 1.003, "discretization_config": DISC,
+                                   "guider_config": {"target": "sgm.modules.diffusionmodules.guiders.LinearCFG", "params": {"scale": 7.5, "scale_min": 4.0}}}},
+        ae_dtype="bf16", diffusion_dtype="bf16", scale_factor=0.13025)
+    with torch.device("cuda"):
+        m = smodel.SUPIRModel(**cfg)
+    m.model.load_state_dict(sd_net)
+    m.first_stage_model.load_state_dict(sd_vae)
+    img = (randn((1, 3, 128, 128), 200) * 0.5).clamp(-1, 1)
+    c = {"crossattn": randn((1, 77, 2048), 201), "vector": randn((1, 2816), 202)}
+    uc = {"crossattn": randn((1, 77, 2048), 203), "vector": randn((1, 2816), 204)}
+    cu = lambda d: {k: v.cuda() for k, v in d.items()}  # noqa: E731
+    steps, seed = 3, 1234
+    monkeypatch.setattr(torch, "randn_like", SeededNoise(5000))
+    out = m.batchify_sample(img.cuda(), num_steps=steps, restoration_scale=4.0, s_churn=5, s_noise=1.01, cfg_scale=4.0, seed=seed,
+                            control_scale=0.9, use_linear_CFG=True, cfg_scale_start=1.0, c=cu(c), uc=cu(uc)).cpu()
+    # ---- the same pipeline from the oracle ----
+    noise = SeededNoise(5000)
+    torch.manual_seed(seed)
+    _z = ovae.gaussian_latent(ovae.encode_moments(sd_vae, img, encoder_prefix="denoise_encoder."), None)
+    x_stage1 = ovae.decode(sd_vae, _z)
+    mom = ovae.encode_moments(sd_vae, x_stage1)
+    z_stage1 = ovae.gaussian_latent(mom, torch.randn(mom.shape[0], 4, *mom.shape[2:]))
+    smp = osamp.RestoreEDMSampler(num_steps=steps, restore_cfg=4.0, s_churn=5, s_noise=1.01, scale=1.0, scale_min=4.0, randn_like=noise)
+    net = lambda x, t, cc, cs: ounet.control_wrapper_forward(sd_net, x, t, cc, cs)  # noqa: E731
+    noised = noise(_z)
+    zs = smp(net, noised, dict(c, control=_z), dict(uc, control=_z), z_stage1, control_scale=0.9)
+    ref = ovae.decode(sd_vae, zs)
+    e = rel_fro(out, ref)
+    print(f"engine end-to-end rel_fro={e:.4g}")
+    assert out.shape == ref.shape and e <= 5e-2
+
+
+@pytest.mark.slow
+def test_full_depth_control_unet_vs_oracle():
+    """The real SUPIR-v0 / SDXL-base layout (transformer depth [1,2,10], 3.87 B parameters) at a 32x32 latent, CFG pair."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from oracle import unet as ounet
+    from supir_b200 import nets, wrappers
+    sd = bench.oracle_state_dict()
+    g = torch.Generator().manual_seed(3)
+    for k, v in sd.items():                      # biases / norm params non-trivial as well
+        if not (k.endswith("weight") and v.dim() >= 2):
+            v.add_(0.05 * torch.randn(v.shape, generator=g))
+    with torch.device("cuda"):
+        unet = nets.LightGLVUNet(mode="XL-base", project_type="ZeroSFT", project_channel_scale=2, **bench.UNET_CFG)
+        ctrl = nets.GLVControl(input_upscale=1, **bench.UNET_CFG)
+    w = wrappers.ControlWrapper(unet, dtype=torch.bfloat16)
+    w.load_control_model(ctrl)
+    w.load_state_dict(sd, strict=True)
+    x = randn((2, 4, 32, 32), 301)
+    cond = {"control": randn((2, 4, 32, 32), 302), "crossattn": randn((2, 77, 2048), 303), "vector": randn((2, 2816), 304)}
+    t = torch.tensor([700, 700])
+    out = w(x.cuda(), t.cuda(), {k: v.cuda() for k, v in cond.items()}, control_scale=1.0).cpu()
+    torch.set_num_threads(min(os.cpu_count() or 1, 64))
+    ref = ounet.control_wrapper_forward(sd, x, t, cond, 1.0)
+    e = rel_fro(out, ref)
+    print(f"full-depth rel_fro={e:.4g}")
+    assert e <= 3e-2
