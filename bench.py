@@ -58,6 +58,15 @@ def peaks():
         return 1400.0, 1590.0, 6650.0, "fallback"
 
 
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")) as f:
+            return json.load(f)["dram_bytes_per_launch_mean"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
 
@@ -306,19 +315,25 @@ def run_supir(args):
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
 
     # ---- VAE passes before sampling (SUPIR_model.py:117-119), timed; e2e includes the image upload ----
+    skip_vae = os.environ.get("SUPIR_BENCH_SKIP_VAE", "0") == "1"     # profiling aid only: invalid as a benchmark number
     barrier()
     e0, e1, e2 = ev(), ev(), ev()
     e0.record()
     img = img_host.to(device, non_blocking=True)
     e1.record()
     from supir_b200.vae import DiagonalGaussianDistribution
-    _z = scale * DiagonalGaussianDistribution(ae.quant_conv(ae.encoder(img))).mode()
-    x_stage1 = ae.decode(1.0 / scale * _z)
-    z_stage1 = scale * ae.encode(x_stage1)
+    if skip_vae:
+        _z = 0.5 * torch.randn(1, 4, LATENT, LATENT, device=device)
+        z_stage1 = 0.5 * torch.randn(1, 4, LATENT, LATENT, device=device)
+    else:
+        _z = scale * DiagonalGaussianDistribution(ae.quant_conv(ae.encoder(img))).mode()
+        x_stage1 = ae.decode(1.0 / scale * _z)
+        z_stage1 = scale * ae.encode(x_stage1)
+        del x_stage1
     e2.record()
     barrier()
     h2d_img_ms, vae_pre_ms = e0.elapsed_time(e1), e1.elapsed_time(e2)
-    del img, x_stage1
+    del img
     cond, ucond = dict(c, control=_z), dict(uc, control=_z)
     noised = torch.randn_like(_z)
     run = smp.begin(denoiser, noised, cond, ucond, x_center=z_stage1, control_scale=1.0)
@@ -360,9 +375,10 @@ def run_supir(args):
     # ---- final decode (SUPIR_model.py:131) + image download ----
     e3, e4, e5 = ev(), ev(), ev()
     e3.record()
-    samples = ae.decode(1.0 / scale * run.x)
+    samples = ae.decode(1.0 / scale * run.x) if not skip_vae else torch.zeros(1, 3, 8, 8, device=device)
     e4.record()
-    out_host.copy_(samples, non_blocking=True)
+    if not skip_vae:
+        out_host.copy_(samples, non_blocking=True)
     e5.record()
     barrier()
     vae_post_ms, d2h_img_ms = e3.elapsed_time(e4), e4.elapsed_time(e5)
@@ -391,7 +407,8 @@ def run_supir(args):
     achieved = g_flops / (g_ms * 1e-3) / 1e12
     roof = {"bound": "tensor", "kernel": "supir::gemm_tcgen05_kernel (Linear / conv1x1 / implicit-GEMM conv3x3)",
             "achieved": achieved, "peak": sust, "peak_kind": f"bf16 dense sustained, {peak_kind}", "unit": "TFLOP/s",
-            "frac": achieved / sust, "traffic": None, "launches_timed": g_n,
+            "frac": achieved / sust, "traffic": load_traffic(), "traffic_unit": "bytes/launch (mean of the ncu --set full capture in profiles/)",
+            "launches_timed": g_n,
             "step_flops": FLOP_WINDOW * 49, "step_achieved_tflops": FLOP_WINDOW * 49 / (step_ms * 1e-3) / 1e12 * (1.0),
             "step_frac_of_peak": FLOP_WINDOW * 49 / (step_ms * 1e-3) / 1e12 / (sust * world)}
     if world == 1 and not args.no_cpu_baseline:
@@ -412,7 +429,7 @@ def run_supir(args):
                                "tiled VAE enc 1024 px / dec 128 latent; SUPIR-v0 + SDXL-base + SDXL-VAE shapes, random weights",
                    "edm_steps": EDM_STEPS, "windows": 49, "tile_batch": smp.tile_batch, "vae_ms": vae_ms, "vae_pre_ms": vae_pre_ms,
                    "vae_post_ms": vae_post_ms, "l2": "per-step working set (7.7 GB of weights + activations) exceeds the 126 MB L2",
-                   "output_finite": finite, "parallelism": f"windows sharded over {world} rank(s), 1 all-gather/step" if world > 1 else "single GPU"},
+                   "output_finite": finite, "vae_skipped_INVALID_FOR_BENCH": skip_vae, "parallelism": f"windows sharded over {world} rank(s), 1 all-gather/step" if world > 1 else "single GPU"},
         "ms_per_edm_step": step_ms,
         "e2e": {"value": MEGAPIXELS / e2e_total_s, "unit": "MP/s", "ms_per_step": e2e_step_ms,
                 "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": int(res_host.numel() * 4),
