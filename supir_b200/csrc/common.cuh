@@ -75,23 +75,25 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 }
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
-// erf-form GELU — F.gelu default used by GEGLU (reference sgm/modules/attention.py:91). erf via Abramowitz-Stegun 7.1.26
-// (|abs err| <= 1.5e-7, far below the bf16 rounding of the result): one MUFU.RCP + one MUFU.EX2 + a degree-5 Horner chain
-// instead of libdevice erff's branchy ~40-instruction sequence, which made the GEGLU epilogue issue-bound.
-__device__ __forceinline__ float erf_as_f(float x) {
-    const float ax = fabsf(x);
-    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+// erf-form GELU — F.gelu default used by GEGLU (reference sgm/modules/attention.py:91):  gelu(g) = g/2 + |g|/2 * erf(|g|/sqrt2).
+// erf via Abramowitz-Stegun 7.1.26 (abs err <= 1.5e-7, far below the bf16 rounding of the result) with 1/sqrt2 folded
+// into the constants: 2 MUFU (rcp, ex2) + 7 FFMA + 4 FMUL, branch-free. libdevice erff (~40 instructions with a slow
+// path) made the GEGLU epilogue issue-bound (profiles/README.md).
+__device__ __forceinline__ float gelu_erf_f(float g) {
+    const float ag = fabsf(g);
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.2316418882f, ag, 1.0f)));   // 1 / (1 + p |g| / sqrt2)
     float poly = fmaf(1.061405429f, t, -1.453152027f);
     poly = fmaf(poly, t, 1.421413741f);
     poly = fmaf(poly, t, -0.284496736f);
     poly = fmaf(poly, t, 0.254829592f);
     poly *= t;
     float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-ax * ax * 1.4426950408889634f));
-    const float r = fmaf(-poly, e, 1.0f);
-    return copysignf(r, x);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(g * g * -0.7213475204f));          // exp(-g^2 / 2)
+    const float erf_abs = fmaf(-poly, e, 1.0f);                                          // erf(|g| / sqrt2)
+    const float h = 0.5f * g;
+    return fmaf(fabsf(h), erf_abs, h);
 }
-__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erf_as_f(x * 0.70710678118654752f)); }
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier
@@ -117,11 +119,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
         ".reg .pred P1;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, P1;\n\t"
         "}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)   // suspend-time hint: the hardware parks the thread instead of spinning
         : "memory");
     return ok != 0;
 }

@@ -256,11 +256,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const float* bc = sb + c * 32;
                 uint4 q[4];
                 if (geglu) {
-                    float o[16];
+                    float o[16], bb[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(&bb[j]) = *reinterpret_cast<const float4*>(bc + j);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const float xv = bf16_round(__uint_as_float(r[j]) + bc[j]);
-                        const float gv = bf16_round(__uint_as_float(r[16 + j]) + bc[16 + j]);
+                        const float xv = bf16_round(__uint_as_float(r[j]) + bb[j]);
+                        const float gv = bf16_round(__uint_as_float(r[16 + j]) + bb[16 + j]);
                         o[j] = xv * bf16_round(gelu_erf_f(gv));
                     }
                     q[0] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
