@@ -173,6 +173,21 @@ int supir_tile_blend(const float* tiles, const int* windows, int num_windows, in
 int supir_gaussian_latent(const float* moments, const float* eps, float scale, float* z, int B, int Cz, long long HW,
                           void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* colour fix on the decoded image (colorfix.cu; SUPIR/utils/colorfix.py)                     */
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* one a-trous wavelet level on fp32 NCHW planes: low = blur(img) with the 3x3 kernel [1 2 1]x[1 2 1]/16 at dilation
+ * `radius` and replicate padding (wavelet_blur, colorfix.py:73-92); high (+)= img - low (wavelet_decomposition :94-106).
+ * high may be NULL; accumulate = 0 overwrites high. img and low must not alias. */
+int supir_wavelet_level(const float* img, float* low, float* high, int planes, int H, int W, int radius, int accumulate,
+                        void* stream);
+/* per-plane (sum, sum of squares) in fp64 -> ws[0 : 2*planes]; deterministic; workspace size from the helper */
+long long supir_plane_stats_workspace(int planes);
+int supir_plane_stats(const float* x, int planes, long long hw, double* ws, long long ws_doubles, void* stream);
+/* adaptive_instance_normalization (colorfix.py:45-71): (content - mean_c) / std_c * std_s + mean_s, unbiased var + 1e-5 */
+int supir_adain_apply(const float* content, const double* content_stats, const double* style_stats, float* out, int planes,
+                      long long hw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -164,18 +164,26 @@ class TiledRestoreEDMSampler(RestoreEDMSampler):
         b, _, h, w = x.shape
         windows = sliding_windows(h, w, self.tile_size, self.tile_stride)
         tile_weights = self.tile_weights.repeat(b, 1, 1, 1)
-        lq = cond["control"]
+        use_local_prompt = isinstance(cond, list)          # one conditioning dict per window (sampling.py:609-617)
+        if use_local_prompt:
+            assert len(cond) == len(windows)
+            cond = [dict(c) for c in cond]
+            lq = cond[0]["control"]
+        else:
+            cond = dict(cond)
+            lq = cond["control"]
+        uc = dict(uc)
         x, s_in, sigmas = self.prepare(x)
-        cond, uc = dict(cond), dict(uc)
         for i in range(len(sigmas) - 1):
             gamma = self.gamma(sigmas, i)
             x_next = torch.zeros_like(x)
             count = torch.zeros_like(x)
             eps_noise = self.randn_like(x)
-            for (hi, he, wi, we) in windows:
-                cond["control"] = lq[:, :, hi:he, wi:we]
+            for j, (hi, he, wi, we) in enumerate(windows):
+                _cond = cond[j] if use_local_prompt else cond
+                _cond["control"] = lq[:, :, hi:he, wi:we]
                 uc["control"] = lq[:, :, hi:he, wi:we]
-                _x = self.sampler_step(network, s_in * sigmas[i], s_in * sigmas[i + 1], x[:, :, hi:he, wi:we], cond, uc,
+                _x = self.sampler_step(network, s_in * sigmas[i], s_in * sigmas[i + 1], x[:, :, hi:he, wi:we], _cond, uc,
                                        gamma, x_center[:, :, hi:he, wi:we], eps_noise=eps_noise[:, :, hi:he, wi:we],
                                        control_scale=control_scale, use_linear_control_scale=use_linear_control_scale,
                                        control_scale_start=control_scale_start)
@@ -183,4 +191,105 @@ class TiledRestoreEDMSampler(RestoreEDMSampler):
                 count[:, :, hi:he, wi:we] += tile_weights
             x_next /= count
             x = x_next
+        return x
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# DPM++ 2M SDE restore samplers (Lightning configs) — sampling.py:271-360 (DPMPP2MSampler), :422-515, :663-730
+# --------------------------------------------------------------------------------------------------------------------
+def get_sigmas_karras(n, sigma_min, sigma_max, rho=7.0):
+    """k-diffusion 0.1.1 `sampling.get_sigmas_karras` (requirements.txt:41; not vendored in the reference): Karras et al.
+    (2022) schedule with an appended zero. Restated from the published formula — parity UNPINNED for this function."""
+    ramp = torch.linspace(0, 1, n)
+    min_inv_rho = sigma_min ** (1 / rho)
+    max_inv_rho = sigma_max ** (1 / rho)
+    sigmas = (max_inv_rho + ramp * (min_inv_rho - max_inv_rho)) ** rho
+    return torch.cat([sigmas, sigmas.new_zeros([1])])
+
+
+class RestoreDPMPP2MSampler:
+    """sampling.py:422-515. `noise_sampler(sigma, sigma_next)` replaces k-diffusion's BrownianTreeNoiseSampler (torchsde is not
+    available): any callable returning unit-variance noise of x's shape."""
+
+    def __init__(self, num_steps, s_noise=1.0, eta=1.0, scale=7.5, scale_min=4.0, noise_sampler=None):
+        self.num_steps, self.s_noise, self.eta = num_steps, s_noise, eta
+        self.scale, self.scale_min = scale, scale_min
+        self.noise_sampler = noise_sampler
+        self.table = denoiser_sigma_table()
+
+    def denoise(self, network, x, sigma, cond, uc, control_scale):
+        xi, si, ci = cfg_prepare_inputs(x, sigma, cond, uc)
+        den = denoise_with_control(network, self.table, xi, si, ci, control_scale)
+        return cfg_combine(den, sigma, self.scale, self.scale_min)
+
+    def sampler_step(self, network, old_denoised, previous_sigma, sigma, next_sigma, x, cond, uc, eps_noise, control_scale):
+        denoised = self.denoise(network, x, sigma, cond, uc, control_scale)
+        t, t_next = sigma.log().neg(), next_sigma.log().neg()
+        h = t_next - t
+        eta_h = self.eta * h
+        d = lambda v: v[:, None, None, None]  # noqa: E731
+        mult1 = t_next.neg().exp() / t.neg().exp() * (-eta_h).exp()
+        mult2 = (-h - eta_h).expm1()
+        x_standard = d(mult1) * x - d(mult2) * denoised
+        if old_denoised is None or torch.sum(next_sigma) < 1e-14:
+            return x_standard, denoised
+        r = (t - previous_sigma.log().neg()) / h
+        denoised_d = d(1 + 1 / (2 * r)) * denoised - d(1 / (2 * r)) * old_denoised
+        x_advanced = d(mult1) * x - d(mult2) * denoised_d
+        x = torch.where(d(next_sigma) > 0.0, x_advanced, x_standard)
+        if self.eta:
+            x = x + eps_noise * d(next_sigma) * d((-2 * eta_h).expm1().neg().sqrt()) * self.s_noise
+        return x, denoised
+
+    def schedule(self, x):
+        sig = legacy_ddpm_sigmas(self.num_steps)
+        x = x * torch.sqrt(1.0 + sig[0] ** 2.0)
+        return x, x.new_ones([x.shape[0]]), get_sigmas_karras(self.num_steps, sig[-2], sig[0]), len(sig)
+
+    def __call__(self, network, x, cond, uc, control_scale=1.0):
+        x, s_in, sigmas, num_sigmas = self.schedule(x)
+        old = None
+        for i in range(num_sigmas - 1):
+            eps = None
+            if i > 0 and torch.sum(s_in * sigmas[i + 1]) > 1e-14:
+                eps = self.noise_sampler(s_in * sigmas[i], s_in * sigmas[i + 1])
+            x, old = self.sampler_step(network, old, None if i == 0 else s_in * sigmas[i - 1], s_in * sigmas[i],
+                                       s_in * sigmas[i + 1], x, cond, uc, eps, control_scale)
+        return x
+
+
+class TiledRestoreDPMPP2MSampler(RestoreDPMPP2MSampler):
+    """sampling.py:663-730."""
+
+    def __init__(self, tile_size=128, tile_stride=64, **kw):
+        super().__init__(**kw)
+        self.tile_size, self.tile_stride = tile_size, tile_stride
+        self.tile_weights = torch.tensor(gaussian_weights(tile_size, tile_size)).repeat(1, 4, 1, 1)
+
+    def __call__(self, network, x, cond, uc, control_scale=1.0):
+        b, _, h, w = x.shape
+        windows = sliding_windows(h, w, self.tile_size, self.tile_stride)
+        tw = self.tile_weights.repeat(b, 1, 1, 1)
+        lq = cond["control"]
+        x, s_in, sigmas, num_sigmas = self.schedule(x)
+        cond, uc = dict(cond), dict(uc)
+        old = None
+        for i in range(num_sigmas - 1):
+            if i > 0 and torch.sum(s_in * sigmas[i + 1]) > 1e-14:
+                eps_noise = self.noise_sampler(s_in * sigmas[i], s_in * sigmas[i + 1])
+            else:
+                eps_noise = torch.zeros_like(x)
+            x_next, old_next, count = torch.zeros_like(x), torch.zeros_like(x), torch.zeros_like(x)
+            for (hi, he, wi, we) in windows:
+                cond["control"] = lq[:, :, hi:he, wi:we]
+                uc["control"] = lq[:, :, hi:he, wi:we]
+                _x, _old = self.sampler_step(network, None if old is None else old[:, :, hi:he, wi:we],
+                                             None if i == 0 else s_in * sigmas[i - 1], s_in * sigmas[i], s_in * sigmas[i + 1],
+                                             x[:, :, hi:he, wi:we], cond, uc, eps_noise[:, :, hi:he, wi:we], control_scale)
+                x_next[:, :, hi:he, wi:we] += _x * tw
+                old_next[:, :, hi:he, wi:we] += _old * tw
+                count[:, :, hi:he, wi:we] += tw
+            old_next /= count
+            x_next /= count
+            x, old = x_next, old_next
         return x

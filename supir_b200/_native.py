@@ -51,6 +51,9 @@ _SIGS = {
     "supir_cfg_combine": [c_void_p, c_void_p, c_void_p, c_int, c_ll, c_void_p],
     "supir_tile_gather": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "supir_tile_blend": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "supir_wavelet_level": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "supir_plane_stats": [c_void_p, c_int, c_ll, c_void_p, c_ll, c_void_p],
+    "supir_adain_apply": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_void_p],
     "supir_gaussian_latent": [c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_ll, c_void_p],
 }
 _SPECIAL = {
@@ -58,6 +61,7 @@ _SPECIAL = {
     "supir_version": ([], c_int),
     "supir_launch_count": ([], c_ll),
     "supir_groupnorm_stats_workspace": ([c_int, c_int, c_int, c_int], c_ll),
+    "supir_plane_stats_workspace": ([c_int], c_ll),
     "supir_reset_launch_count": ([], None),
 }
 

@@ -19,6 +19,8 @@ PATCHES = {
     "sgm.modules.diffusionmodules.sampling": {
         "RestoreEDMSampler": "supir_b200.sampling:RestoreEDMSampler",
         "TiledRestoreEDMSampler": "supir_b200.sampling:TiledRestoreEDMSampler",
+        "RestoreDPMPP2MSampler": "supir_b200.sampling:RestoreDPMPP2MSampler",
+        "TiledRestoreDPMPP2MSampler": "supir_b200.sampling:TiledRestoreDPMPP2MSampler",
         "gaussian_weights": "supir_b200.sampling:gaussian_weights",
         "_sliding_windows": "supir_b200.sampling:_sliding_windows",
     },
@@ -28,7 +30,9 @@ PATCHES = {
                                "AutoencoderKL": "supir_b200.vae:AutoencoderKL"},
     "SUPIR.utils.tilevae": {"VAEHook": "supir_b200.vae:VAEHook"},
     "SUPIR.models.SUPIR_model": {"VAEHook": "supir_b200.vae:VAEHook",
-                                 "DiagonalGaussianDistribution": "supir_b200.vae:DiagonalGaussianDistribution"},
+                                 "DiagonalGaussianDistribution": "supir_b200.vae:DiagonalGaussianDistribution",
+                                 "wavelet_reconstruction": "supir_b200.colorfix:wavelet_reconstruction",
+                                 "adaptive_instance_normalization": "supir_b200.colorfix:adaptive_instance_normalization"},
 }
 
 

@@ -19,6 +19,8 @@ _ALIASES = {
     "sgm.modules.diffusionmodules.sampling_utils.NoDynamicThresholding": "supir_b200.guiders.NoDynamicThresholding",
     "sgm.modules.diffusionmodules.sampling.RestoreEDMSampler": "supir_b200.sampling.RestoreEDMSampler",
     "sgm.modules.diffusionmodules.sampling.TiledRestoreEDMSampler": "supir_b200.sampling.TiledRestoreEDMSampler",
+    "sgm.modules.diffusionmodules.sampling.RestoreDPMPP2MSampler": "supir_b200.sampling.RestoreDPMPP2MSampler",
+    "sgm.modules.diffusionmodules.sampling.TiledRestoreDPMPP2MSampler": "supir_b200.sampling.TiledRestoreDPMPP2MSampler",
     "SUPIR.modules.SUPIR_v0.GLVControl": "supir_b200.nets.GLVControl",
     "SUPIR.modules.SUPIR_v0.LightGLVUNet": "supir_b200.nets.LightGLVUNet",
     "sgm.models.autoencoder.AutoencoderKLInferenceWrapper": "supir_b200.vae.AutoencoderKLInferenceWrapper",

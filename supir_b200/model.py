@@ -110,8 +110,6 @@ class SUPIRModel(nn.Module):
         """x: [N, 3, H, W] in [-1, 1]. `c` / `uc` (dicts with 'crossattn' [N,77,2048] and 'vector' [N,2816]) replace the
         text conditioner when given; 'control' is filled in here like prepare_condition does."""
         assert color_fix_type in ["Wavelet", "AdaIn", "None"]
-        if color_fix_type != "None":
-            raise NotImplementedError("colour fix is post-processing outside the accelerated hot path (SURVEY.md §8f)")
         N = len(x)
         if num_samples > 1:
             assert N == 1
@@ -133,4 +131,11 @@ class SUPIRModel(nn.Module):
         noised_z = torch.randn_like(_z).to(_z.device)
         _samples = self.sampler(denoiser, noised_z, cond=c, uc=uc, x_center=z_stage1, control_scale=control_scale,
                                 use_linear_control_scale=use_linear_control_scale, control_scale_start=control_scale_start)
-        return self.decode_first_stage(_samples)
+        samples = self.decode_first_stage(_samples)
+        if color_fix_type == "Wavelet":
+            from .colorfix import wavelet_reconstruction
+            samples = wavelet_reconstruction(samples, x_stage1)
+        elif color_fix_type == "AdaIn":
+            from .colorfix import adaptive_instance_normalization
+            samples = adaptive_instance_normalization(samples, x_stage1)
+        return samples

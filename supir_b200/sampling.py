@@ -294,3 +294,157 @@ class _TiledRun:
         ops.tile_blend(self.tiles_out, self.table_dev, T, self.weights64, x_next)
         self.x = x_next
         return x_next
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# DPM++ 2M SDE restore samplers (SUPIR_v0_Juggernautv9_lightning.yaml) — reference sampling.py:271-360, 422-515, 663-730
+# ----------------------------------------------------------------------------------------------------------------------
+def get_sigmas_karras(n, sigma_min, sigma_max, rho=7.0, device="cpu"):
+    """k-diffusion 0.1.1 `get_sigmas_karras` (the reference imports it, sampling.py:20; the package is not vendored):
+    Karras et al. 2022 schedule with an appended zero, restated from the published formula."""
+    ramp = torch.linspace(0, 1, n)
+    min_inv_rho = float(sigma_min) ** (1 / rho)
+    max_inv_rho = float(sigma_max) ** (1 / rho)
+    sigmas = (max_inv_rho + ramp * (min_inv_rho - max_inv_rho)) ** rho
+    return torch.cat([sigmas, sigmas.new_zeros([1])]).to(device)
+
+
+class BrownianIncrementNoise:
+    """Stand-in for k-diffusion's BrownianTreeNoiseSampler (torchsde): the reference asks it for the normalised Brownian
+    increment between two sigmas, once per step, on disjoint intervals — i.e. independent N(0, I) draws. This class draws
+    them with torch.randn_like (same distribution; NOT the same numbers for a given seed: parity unpinned)."""
+
+    def __init__(self, x, sigma_min=None, sigma_max=None):
+        self.like = x
+
+    def __call__(self, sigma, sigma_next):
+        return torch.randn_like(self.like)
+
+
+class RestoreDPMPP2MSampler(BaseDiffusionSampler):
+    noise_sampler_cls = BrownianIncrementNoise
+
+    def __init__(self, s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0, restore_cfg=4.0, restore_cfg_s_tmin=0.05,
+                 eta=1.0, *args, **kwargs):
+        self.s_noise, self.eta = s_noise, eta
+        super().__init__(*args, **kwargs)
+
+    # host-side float32 step multipliers (get_variables / get_mult, sampling.py:290-315, 435-446)
+    def step_multipliers(self, sigma, next_sigma, previous_sigma):
+        with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+            t, t_next = f32(-np.log(f32(sigma))), f32(-np.log(f32(next_sigma)))
+            h = f32(t_next - t)
+            eta_h = f32(self.eta) * h
+            m1 = f32(np.exp(-t_next) / np.exp(-t) * np.exp(-eta_h))
+            m2 = f32(np.expm1(-h - eta_h))
+            m3 = m4 = None
+            if previous_sigma is not None:
+                r = f32((t - f32(-np.log(f32(previous_sigma)))) / h)
+                m3, m4 = f32(1 + 1 / (2 * r)), f32(1 / (2 * r))
+            noise_mul = f32(next_sigma) * f32(np.sqrt(-np.expm1(-2 * eta_h))) * f32(self.s_noise)
+        return float(m1), float(m2), (None if m3 is None else float(m3)), (None if m4 is None else float(m4)), float(noise_mul)
+
+    def _denoise(self, denoiser, x, sigma, cond, uc, control_scale):
+        N = x.shape[0]
+        if isinstance(denoiser, FusedDenoiser) and hasattr(self.guider, "scale_host"):
+            sq, idx = denoiser.denoiser.quantize_host(sigma)
+            c_in = float(f32(1.0) / np.sqrt(f32(sq) * f32(sq) + f32(1.0)))
+            x_hat = torch.empty_like(x)
+            net_in = torch.empty((2 * N,) + tuple(x.shape[1:]), dtype=torch.float32, device=x.device)
+            ops.edm_pre(x, None, 0.0, c_in, x_hat, net_in)
+            cpair = {key: torch.cat((uc[key], cond[key]), 0) for key in ("vector", "crossattn", "control")}
+            t = torch.full((2 * N,), idx, dtype=torch.long, device=x.device)
+            net_out = denoiser.network(net_in, t, cpair, control_scale)
+            den, scratch = torch.empty_like(x), torch.empty_like(x)
+            ops.edm_post(x_hat, net_out, None, -sq, self.guider.scale_host(sigma), 0.0, 1.0, 0.0, scratch, denoised=den)
+            return den
+        st = torch.full((N,), sigma, dtype=torch.float32, device=x.device)
+        xi, si, ci = self.guider.prepare_inputs(x, st, cond, uc)
+        return self.guider(denoiser(xi, si, ci, control_scale), st).contiguous()
+
+    def sampler_step(self, denoiser, old_denoised, previous_sigma, sigma, next_sigma, x, cond, uc, eps_noise, control_scale):
+        denoised = self._denoise(denoiser, x, sigma, cond, uc, control_scale)
+        m1, m2, m3, m4, noise_mul = self.step_multipliers(sigma, next_sigma, previous_sigma)
+        out = torch.empty_like(x)
+        if old_denoised is None or next_sigma < 1e-14:
+            ops.axpby_f32(x, m1, denoised, -m2, out)
+            return out, denoised
+        dd = torch.empty_like(x)
+        ops.axpby_f32(denoised, m3, old_denoised.contiguous(), -m4, dd)
+        ops.axpby_f32(x, m1, dd, -m2, out)
+        if self.eta:
+            ops.axpby_f32(out, 1.0, eps_noise.contiguous(), noise_mul, dd)
+            out = dd
+        return out, denoised
+
+    def _schedule(self, x, num_steps):
+        sig = self.host_sigmas(num_steps)
+        x0 = torch.empty_like(x, dtype=torch.float32)
+        ops.axpby_f32(x.contiguous().float(), float(np.sqrt(f32(1.0) + sig[0] * sig[0])), None, 0.0, x0)
+        n = self.num_steps if num_steps is None else num_steps
+        return x0, get_sigmas_karras(n, sig[-2], sig[0]).numpy().astype(np.float32), len(sig)
+
+    @torch.no_grad()
+    def __call__(self, denoiser, x, cond, uc=None, num_steps=None, control_scale=1.0, **kwargs):
+        uc = cond if uc is None else uc
+        x, sigmas, num_sigmas = self._schedule(x, num_steps)
+        noise = self.noise_sampler_cls(x, sigmas[-2], sigmas[0])
+        old = None
+        for i in range(num_sigmas - 1):
+            eps = noise(sigmas[i], sigmas[i + 1]) if (i > 0 and sigmas[i + 1] > 1e-14) else None
+            x, old = self.sampler_step(denoiser, old, None if i == 0 else float(sigmas[i - 1]), float(sigmas[i]),
+                                       float(sigmas[i + 1]), x, cond, uc, eps, control_scale)
+        return x
+
+
+class TiledRestoreDPMPP2MSampler(RestoreDPMPP2MSampler):
+    def __init__(self, tile_size=128, tile_stride=64, tile_batch=8, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.tile_size, self.tile_stride, self.tile_batch = tile_size, tile_stride, max(1, int(tile_batch))
+        self._weights = None
+
+    @torch.no_grad()
+    def __call__(self, denoiser, x, cond, uc=None, num_steps=None, control_scale=1.0, **kwargs):
+        use_local_prompt = isinstance(cond, list)
+        b, ch, h, w = x.shape
+        T = self.tile_size
+        windows = _sliding_windows(h, w, T, self.tile_stride)
+        nw = len(windows)
+        lq = (cond[0] if use_local_prompt else cond)["control"].contiguous().float()
+        uc = (cond[0] if use_local_prompt else cond) if uc is None else uc
+        if self._weights is None:
+            self._weights = gaussian_weights(T, T, 1, device=self.device)
+        w64 = self._weights[0, 0].contiguous()
+        table = torch.tensor(windows, dtype=torch.int32, device=x.device)
+        x, sigmas, num_sigmas = self._schedule(x, num_steps)
+        noise = self.noise_sampler_cls(x, sigmas[-2], sigmas[0])
+        lq_t = torch.empty((nw, b, ch, T, T), dtype=torch.float32, device=x.device)
+        ops.tile_gather(lq, table, T, lq_t)
+        old = None
+        for i in range(num_sigmas - 1):
+            has_noise = i > 0 and sigmas[i + 1] > 1e-14
+            eps_noise = noise(sigmas[i], sigmas[i + 1]) if has_noise else torch.zeros_like(x)
+            x_t, e_t = torch.empty_like(lq_t), torch.empty_like(lq_t)
+            ops.tile_gather(x, table, T, x_t)
+            ops.tile_gather(eps_noise.contiguous(), table, T, e_t)
+            o_t = None
+            if old is not None:
+                o_t = torch.empty_like(lq_t)
+                ops.tile_gather(old, table, T, o_t)
+            xs, ds = torch.empty_like(lq_t), torch.empty_like(lq_t)
+            for g0, g1 in balanced_groups(nw, self.tile_batch):
+                g = g1 - g0
+                flat = lambda t_: t_[g0:g1].reshape(g * b, ch, T, T)  # noqa: E731
+                c_g = {"control": flat(lq_t),
+                       "crossattn": torch.cat([(cond[j] if use_local_prompt else cond)["crossattn"] for j in range(g0, g1)], 0),
+                       "vector": torch.cat([(cond[j] if use_local_prompt else cond)["vector"] for j in range(g0, g1)], 0)}
+                uc_g = {"control": c_g["control"], "crossattn": torch.cat([uc["crossattn"]] * g, 0), "vector": torch.cat([uc["vector"]] * g, 0)}
+                _x, _d = self.sampler_step(denoiser, None if o_t is None else flat(o_t), None if i == 0 else float(sigmas[i - 1]),
+                                           float(sigmas[i]), float(sigmas[i + 1]), flat(x_t), c_g, uc_g, flat(e_t), control_scale)
+                xs[g0:g1] = _x.view(g, b, ch, T, T)
+                ds[g0:g1] = _d.view(g, b, ch, T, T)
+            x_next, old_next = torch.empty_like(x), torch.empty_like(x)
+            ops.tile_blend(xs, table, T, w64, x_next)
+            ops.tile_blend(ds, table, T, w64, old_next)
+            x, old = x_next, old_next
+        return x

@@ -258,3 +258,16 @@ def test_gemm_conv_attention_vs_torch():
     qh, kh, vh = (t.float().view(B, -1, heads, 64).transpose(1, 2) for t in (q, k, v))
     ref = F.scaled_dot_product_attention(qh, kh, vh).transpose(1, 2).reshape(B * L, -1)
     close(att.float().cpu(), ref, 2e-2)
+
+
+def test_colorfix_vs_reference_golden():
+    """fp32 image-space ops: 2e-5 against the reference's own outputs."""
+    import os
+    from supir_b200 import colorfix
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "colorfix.npz"))
+    content, style = rnd((1, 3, 70, 90), 900) * 0.5, rnd((1, 3, 70, 90), 901) * 0.5 + 0.1
+    hi, lo = colorfix.wavelet_decomposition(content.cuda())
+    close(hi.cpu(), torch.from_numpy(g["high"]), 2e-5, 1e-5)
+    close(lo.cpu(), torch.from_numpy(g["low"]), 2e-5, 1e-5)
+    close(colorfix.wavelet_reconstruction(content.cuda(), style.cuda()).cpu(), torch.from_numpy(g["wavelet"]), 2e-5, 1e-5)
+    close(colorfix.adaptive_instance_normalization(content.cuda(), style.cuda()).cpu(), torch.from_numpy(g["adain"]), 2e-5, 1e-5)

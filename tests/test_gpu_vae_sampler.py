@@ -102,3 +102,44 @@ def test_samplers_with_toy_network_match_reference(monkeypatch):
             monkeypatch.setattr(torch, "randn_like", SeededNoise(2000))
             out = smp(denoiser, x.cuda(), cond=cu(c), uc=cu(uc), x_center=xc.cuda(), control_scale=1.0).cpu()
             torch.testing.assert_close(out, torch.from_numpy(g["tiled"]), rtol=1e-4, atol=1e-4)
+            # per-window prompts (cond is a list, one dict per window)
+            nwin = len(sampling._sliding_windows(40, 28, 16, 8))
+            conds = [cu({"control": c["control"], "vector": randn((1, 6), 700 + j), "crossattn": randn((1, 3, 5), 800 + j)}) for j in range(nwin)]
+            monkeypatch.setattr(torch, "randn_like", SeededNoise(2500))
+            out = smp(denoiser, x.cuda(), cond=conds, uc=cu(uc), x_center=xc.cuda(), control_scale=1.0).cpu()
+            torch.testing.assert_close(out, torch.from_numpy(g["tiled_local"]), rtol=1e-4, atol=1e-4)
+
+
+def test_dpmpp_samplers_match_reference():
+    """DPM++ 2M SDE restore samplers (Lightning config): 1e-4 against the reference's runs with the same injected noise."""
+    from supir_b200 import sampling
+    g = np.load(os.path.join(G, "sampler_dpmpp_toy.npz"))
+    den = make_denoiser()
+    guider = {"target": "sgm.modules.diffusionmodules.guiders.LinearCFG", "params": {"scale": 2.0, "scale_min": 2.0}}
+    cu = lambda d: {k: v.cuda() for k, v in d.items()}  # noqa: E731
+
+    class Brownian:
+        def __init__(self, x, a=None, b=None):
+            self.shape, self.n = tuple(x.shape), 0
+
+        def __call__(self, a, b):
+            self.n += 1
+            return randn(self.shape, 3000 + self.n).cuda()
+
+    for fused in (False, True):
+        denoiser = sampling.FusedDenoiser(den, toy_network) if fused else (lambda x, s, c, cs: den(toy_network, x, s, c, cs))
+        smp = sampling.RestoreDPMPP2MSampler(num_steps=5, s_noise=1.003, eta=1.0, discretization_config=DISC, guider_config=guider)
+        smp.noise_sampler_cls = Brownian
+        x = randn((1, 4, 12, 10), 70)
+        c = {"control": randn((1, 4, 12, 10), 71), "vector": randn((1, 6), 72), "crossattn": randn((1, 3, 5), 73)}
+        uc = {"control": c["control"], "vector": randn((1, 6), 74), "crossattn": randn((1, 3, 5), 75)}
+        out = smp(denoiser, x.cuda(), cond=cu(c), uc=cu(uc), control_scale=0.9).cpu()
+        torch.testing.assert_close(out, torch.from_numpy(g["dpmpp"]), rtol=1e-4, atol=1e-4)
+        smp = sampling.TiledRestoreDPMPP2MSampler(tile_size=16, tile_stride=8, tile_batch=3, num_steps=4, s_noise=1.003, eta=1.0,
+                                                  discretization_config=DISC, guider_config=guider)
+        smp.noise_sampler_cls = Brownian
+        x = randn((1, 4, 40, 28), 80)
+        c = {"control": randn((1, 4, 40, 28), 81), "vector": randn((1, 6), 82), "crossattn": randn((1, 3, 5), 83)}
+        uc = {"control": c["control"], "vector": randn((1, 6), 84), "crossattn": randn((1, 3, 5), 85)}
+        out = smp(denoiser, x.cuda(), cond=cu(c), uc=cu(uc), control_scale=1.0).cpu()
+        torch.testing.assert_close(out, torch.from_numpy(g["dpmpp_tiled"]), rtol=1e-4, atol=1e-4)

@@ -124,6 +124,11 @@ def test_samplers_toy_network():
     xc = randn((1, 4, 40, 28), 66)
     out = smp(toy_network, x, c, uc, xc, control_scale=1.0)
     torch.testing.assert_close(out, torch.from_numpy(g["tiled"]), rtol=1e-5, atol=1e-5)
+    nwin = len(osamp.sliding_windows(40, 28, 16, 8))
+    conds = [{"control": c["control"], "vector": randn((1, 6), 700 + j), "crossattn": randn((1, 3, 5), 800 + j)} for j in range(nwin)]
+    smp.randn_like = SeededNoise(2500)
+    out = smp(toy_network, x, conds, uc, xc, control_scale=1.0)
+    torch.testing.assert_close(out, torch.from_numpy(g["tiled_local"]), rtol=1e-5, atol=1e-5)
 
 
 def test_vae_tiny_untiled_and_tiled():
@@ -154,3 +159,40 @@ def test_unet_fullwidth_depth1():
     out = ounet.light_glv_unet_forward(sd, x, t, cond["crossattn"], cond["vector"], control, 0.8, cfg["model_channels"],
                                        cfg["num_head_channels"], prefix="diffusion_model.")
     torch.testing.assert_close(out, torch.from_numpy(g["out"]), rtol=1e-3, atol=1e-3)
+
+
+def test_colorfix_oracle():
+    from oracle import colorfix as oc
+    g = np.load(os.path.join(G, "colorfix.npz"))
+    content, style = randn((1, 3, 70, 90), 900) * 0.5, randn((1, 3, 70, 90), 901) * 0.5 + 0.1
+    hi, lo = oc.wavelet_decomposition(content)
+    torch.testing.assert_close(hi, torch.from_numpy(g["high"]), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(lo, torch.from_numpy(g["low"]), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(oc.wavelet_reconstruction(content, style), torch.from_numpy(g["wavelet"]), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(oc.adaptive_instance_normalization(content, style), torch.from_numpy(g["adain"]), rtol=1e-5, atol=1e-6)
+
+
+class SeededBrownian:
+    def __init__(self, shape):
+        self.shape, self.n = shape, 0
+
+    def __call__(self, a, b):
+        self.n += 1
+        return randn(self.shape, 3000 + self.n)
+
+
+def test_dpmpp_samplers_toy_network():
+    """Step arithmetic of the DPM++ restore samplers is pinned on the reference; the Karras schedule and the Brownian noise
+    come from outside the reference (k-diffusion) and are supplied identically to both sides."""
+    g = np.load(os.path.join(G, "sampler_dpmpp_toy.npz"))
+    smp = osamp.RestoreDPMPP2MSampler(num_steps=5, s_noise=1.003, eta=1.0, scale=2.0, scale_min=2.0, noise_sampler=SeededBrownian((1, 4, 12, 10)))
+    x = randn((1, 4, 12, 10), 70)
+    c = {"control": randn((1, 4, 12, 10), 71), "vector": randn((1, 6), 72), "crossattn": randn((1, 3, 5), 73)}
+    uc = {"control": c["control"], "vector": randn((1, 6), 74), "crossattn": randn((1, 3, 5), 75)}
+    torch.testing.assert_close(smp(toy_network, x, c, uc, control_scale=0.9), torch.from_numpy(g["dpmpp"]), rtol=1e-5, atol=1e-5)
+    smp = osamp.TiledRestoreDPMPP2MSampler(tile_size=16, tile_stride=8, num_steps=4, s_noise=1.003, eta=1.0, scale=2.0, scale_min=2.0,
+                                           noise_sampler=SeededBrownian((1, 4, 40, 28)))
+    x = randn((1, 4, 40, 28), 80)
+    c = {"control": randn((1, 4, 40, 28), 81), "vector": randn((1, 6), 82), "crossattn": randn((1, 3, 5), 83)}
+    uc = {"control": c["control"], "vector": randn((1, 6), 84), "crossattn": randn((1, 3, 5), 85)}
+    torch.testing.assert_close(smp(toy_network, x, c, uc, control_scale=1.0), torch.from_numpy(g["dpmpp_tiled"]), rtol=1e-5, atol=1e-5)
