@@ -522,6 +522,19 @@ int main(int argc, char** argv) {
         perf_attention(2, 10, 4096, 77);
         perf_attention(2, 20, 1024, 77);
     }
+    if (what == "sanitize") {   // small cases for compute-sanitizer (memcheck / racecheck / synccheck)
+        for (int bn : {0, 64, 160}) {
+            supir_set_gemm_tile_n(bn);
+            test_gemm(300, 200, 192, 0, true, true, false, 0);
+            test_gemm(130, 328, 320, 1, true, false, true, 0);
+            test_gemm(200, 256, 128, 2, true, false, false, 0);
+        }
+        supir_set_gemm_tile_n(0);
+        test_conv(2, 32, 32, 64, 128, 0, true, true);
+        test_conv(1, 17, 23, 72, 40, 0, false, false);
+        test_attention(2, 3, 200, 77, 0);
+        test_attention(1, 2, 333, 500, 0);
+    }
     if (what == "perf3" || what == "all") {
         perf_gemm_variants(14336, 10240, 1280, 2);
         perf_gemm_variants(14336, 1280, 1280, 0);
