@@ -55,6 +55,10 @@ int supir_conv3x3_bf16(const void* x, long long ldx, const void* Wp, void* out, 
 
 /* debugging / tuning knob: force the N tile (64/128/256), 0 = heuristic */
 int supir_set_gemm_tile_n(int bn);
+/* tuning knob: the widest tile can run on CTA pairs (2-CTA clusters, tcgen05 cta_group::2: a 256 x 256 tile per pair,
+ * each CTA staging half of the W tile). 0 = single-CTA kernel everywhere, 1 = pairs where they measured faster (default;
+ * also settable through the environment variable SUPIR_B200_GEMM_PAIR), 2 = pairs whenever the tile is 256 wide */
+int supir_set_gemm_pair_mode(int on);
 /* debugging: 1 routes every GEMM through the direct-store epilogue instead of the shared-memory + TMA-store one */
 int supir_debug_force_direct_epilogue(int on);
 /* debugging: override the UMMA shared-memory descriptor template / instruction descriptor (-1 = built-in default) */

@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "supir_b200.h"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace supir {
@@ -47,6 +48,7 @@ struct GemmKernelParams {
     long long ldc;
     int out_f32;
     int n_out;            // valid output columns (N or N/2 for GEGLU)
+    int nimg;             // conv mode: number of images (patches beyond it are padding of the last CTA pair)
     int staged;           // 1: epilogue through shared memory (bias tile in smem, TMA-loaded residual, TMA store)
     int has_res;          // staged path: residual tensor map valid
     uint32_t desc_hi;     // upper 32 bits of the shared-memory matrix descriptor (SBO / version / swizzle mode)
@@ -54,12 +56,12 @@ struct GemmKernelParams {
     uint32_t idesc;       // tcgen05 instruction descriptor
 };
 
-template <int BN>
+template <int BN, int CTAS = 1>
 struct GemmSmem {
     static constexpr int A_BYTES = BM * BK * 2;
-    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int B_BYTES = (BN / CTAS) * BK * 2;   // a CTA pair splits the B tile
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 3 : (BN == 160 ? 4 : (BN == 128 ? 4 : 6));
+    static constexpr int STAGES = CTAS == 2 ? 4 : ((BN == 256) ? 3 : (BN == 160 ? 4 : (BN == 128 ? 4 : 6)));
     // epilogue staging: per half-group (4 warps = 128 rows) two 8 KB output buffers and two 8 KB residual buffers
     // (128 rows x 32 bf16 columns, 64B-swizzled), plus the tile's bias (+ per-image vector) for both accumulators
     static constexpr int CH_BYTES = BM * 32 * 2;
@@ -70,13 +72,18 @@ struct GemmSmem {
     static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
 };
 
-template <int BN>
+template <int BN, int CTAS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                     const GemmKernelParams p) {
-    using S = GemmSmem<BN>;
+    using S = GemmSmem<BN, CTAS>;
     constexpr int STAGES = S::STAGES;
+    // CTAS == 2: two CTAs of a cluster work on one 256 x BN tile (tcgen05 cta_group::2). CTA `cta_rank` owns rows
+    // [rank*128, rank*128+128) of the tile and loads its own A tile and its half of the B tile; CTA 0 issues the MMAs.
+    const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0;
+    const int tile_start = CTAS == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_step = CTAS == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
@@ -103,7 +110,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], 8);  // one arrive per epilogue warp
+            mbar_init(&tmem_empty[a], 8 * CTAS);  // one arrive per epilogue warp (of both CTAs of a pair)
         }
         for (int a = 0; a < 4; ++a) mbar_init(&res_full[a], 1);
         if (p.staged) {
@@ -113,11 +120,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_ptr, S::TMEM_COLS);
-        tmem_relinquish();
+        if (CTAS == 2) { tmem_alloc_2sm(tmem_ptr, S::TMEM_COLS); tmem_relinquish_2sm(); }
+        else { tmem_alloc(tmem_ptr, S::TMEM_COLS); tmem_relinquish(); }
     }
     tc_fence_before();
     __syncthreads();
+    if (CTAS == 2) cluster_sync_all();     // the peer's barriers must be initialised before any remote arrive / TMA credit
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
@@ -126,44 +134,57 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // ===================== TMA producer =====================
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile_start; tile < num_tiles; tile += tile_step) {
                 const int mt = p.m_fastest ? tile % p.num_m_tiles : tile / p.num_n_tiles;
                 const int nt = p.m_fastest ? tile / p.num_m_tiles : tile % p.num_n_tiles;
+                const int rt = mt * CTAS + (int)cta_rank;          // 128-row tile handled by this CTA
                 int b = 0, y0 = 0, x0 = 0;
                 if (p.conv) {
                     const int per_img = p.tiles_x * p.tiles_y;
-                    b = mt / per_img;
-                    const int r = mt % per_img;
+                    b = rt / per_img;
+                    const int r = rt % per_img;
                     y0 = (r / p.tiles_x) * p.TH;
                     x0 = (r % p.tiles_x) * p.TW;
                 }
+                const int bn0 = nt * BN + (int)cta_rank * (BN / CTAS);   // first W row of this CTA's share of the B tile
                 for (int kb = 0; kb < p.num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+                    if (CTAS == 1 || cta_rank == 0) mbar_expect_tx(&full_bar[stage], CTAS * S::STAGE_BYTES);
+                    uint8_t* sa = smem_a + stage * S::A_BYTES;
+                    uint8_t* sb = smem_b + stage * S::B_BYTES;
                     if (p.conv) {
                         const int tap = kb / p.kchunks;
                         const int cc = kb - tap * p.kchunks;
                         const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-                        tma_load_4d(smem_a + stage * S::A_BYTES, &tmA, &full_bar[stage], cc * BK, x0 + dx, y0 + dy, b);
-                        tma_load_2d(smem_b + stage * S::B_BYTES, &tmB, &full_bar[stage], tap * p.Cin + cc * BK,
-                                    nt * BN);
+                        if (CTAS == 2) {
+                            tma_load_4d_2sm(sa, &tmA, &full_bar[stage], cc * BK, x0 + dx, y0 + dy, b);
+                            tma_load_2d_2sm(sb, &tmB, &full_bar[stage], tap * p.Cin + cc * BK, bn0);
+                        } else {
+                            tma_load_4d(sa, &tmA, &full_bar[stage], cc * BK, x0 + dx, y0 + dy, b);
+                            tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.Cin + cc * BK, bn0);
+                        }
                     } else {
-                        tma_load_2d(smem_a + stage * S::A_BYTES, &tmA, &full_bar[stage], kb * BK, mt * BM);
-                        tma_load_2d(smem_b + stage * S::B_BYTES, &tmB, &full_bar[stage], kb * BK, nt * BN);
+                        if (CTAS == 2) {
+                            tma_load_2d_2sm(sa, &tmA, &full_bar[stage], kb * BK, rt * BM);
+                            tma_load_2d_2sm(sb, &tmB, &full_bar[stage], kb * BK, bn0);
+                        } else {
+                            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, rt * BM);
+                            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, bn0);
+                        }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===================== MMA issuer =====================
+        if (lane == 0 && cta_rank == 0) {
+            // ===================== MMA issuer (CTA 0 of a pair issues for both) =====================
             const uint32_t idesc = p.idesc;
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile_start; tile < num_tiles; tile += tile_step) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * S::ACC_STRIDE;
@@ -176,12 +197,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         // advance 16 k-elements = 32 bytes inside the 128B swizzle atom: +2 in the (addr>>4) field
-                        umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        if (CTAS == 2) umma_bf16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        else umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
                     }
-                    umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
+                    // smem slot free (in both CTAs of a pair) once these MMAs retire
+                    if (CTAS == 2) umma_commit_2sm(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tmem_full[acc]);
+                if (CTAS == 2) umma_commit_2sm(&tmem_full[acc], 3); else umma_commit(&tmem_full[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -208,14 +231,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         int acc = 0;
         uint32_t acc_phase = 0;
         constexpr int NCH = BN / 32;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = tile_start; tile < num_tiles; tile += tile_step) {
             const int mt = p.m_fastest ? tile % p.num_m_tiles : tile / p.num_n_tiles;
             const int nt = p.m_fastest ? tile / p.num_m_tiles : tile % p.num_n_tiles;
+            const int rt = mt * CTAS + (int)cta_rank;
             int cb = 0, cy0 = 0, cx0 = 0;
             if (p.conv) {
                 const int per_img = p.tiles_x * p.tiles_y;
-                cb = mt / per_img;
-                const int r = mt % per_img;
+                cb = rt / per_img;
+                const int r = rt % per_img;
                 cy0 = (r / p.tiles_x) * p.TH;
                 cx0 = (r % p.tiles_x) * p.TW;
             }
@@ -227,7 +251,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             auto issue_res = [&](int k, int buf) {
                 mbar_expect_tx(&my_res_full[buf], BM * 64);
                 if (p.conv) tma_load_4d(stage_r + buf * S::CH_BYTES, &tmR, &my_res_full[buf], out_col(k), cx0, cy0, cb);
-                else tma_load_2d(stage_r + buf * S::CH_BYTES, &tmR, &my_res_full[buf], out_col(k), mt * BM);
+                else tma_load_2d(stage_r + buf * S::CH_BYTES, &tmR, &my_res_full[buf], out_col(k), rt * BM);
             };
             // tile prologue: bias (+ per-image vector) for the tile's columns; first two residual chunks
             float* sb = s_bias + acc * BN;
@@ -236,7 +260,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 float b = 0.f;
                 if (n < p.N) {
                     if (p.bias) b = __ldg(p.bias + n);
-                    if (p.rowvec) b += __ldg(p.rowvec + (long long)cb * p.rowvec_ld + n);
+                    if (p.rowvec && cb < p.nimg) b += __ldg(p.rowvec + (long long)cb * p.rowvec_ld + n);
                 }
                 sb[epi_tid] = b;
             }
@@ -317,7 +341,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 named_bar_sync(1 + h, 128);
                 if (elected) {
                     if (p.conv) tma_store_4d(&tmC, stage_c + buf * S::CH_BYTES, out_col(k), cx0, cy0, cb);
-                    else tma_store_2d(&tmC, stage_c + buf * S::CH_BYTES, out_col(k), mt * BM);
+                    else tma_store_2d(&tmC, stage_c + buf * S::CH_BYTES, out_col(k), rt * BM);
                     bulk_commit_group();
                     if (p.has_res && k + 2 < nck) issue_res(k + 2, buf);
                 }
@@ -326,15 +350,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int k = 0; k < nck; k += 2) {
                 tmem_ld_wait();
                 if (k + 1 < nck) tmem_ld_32x32(t_row + (h + 2 * (k + 1)) * 32, rb);
-                else { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&tmem_empty[acc]); }
+                else { tc_fence_before(); __syncwarp(); if (lane == 0) { if (CTAS == 2 && cta_rank != 0) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); } }
                 finish(ra, k);
                 if (k + 1 >= nck) break;
                 tmem_ld_wait();
                 if (k + 2 < nck) tmem_ld_32x32(t_row + (h + 2 * (k + 2)) * 32, ra);
-                else { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&tmem_empty[acc]); }
+                else { tc_fence_before(); __syncwarp(); if (lane == 0) { if (CTAS == 2 && cta_rank != 0) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); } }
                 finish(rb, k + 1);
             }
-            if (nck == 0) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&tmem_empty[acc]); }
+            if (nck == 0) { tc_fence_before(); __syncwarp(); if (lane == 0) { if (CTAS == 2 && cta_rank != 0) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); } }
             cnt += nck;
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
@@ -345,24 +369,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int row_in_tile = quad * 32 + lane;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = tile_start; tile < num_tiles; tile += tile_step) {
             const int mt = p.m_fastest ? tile % p.num_m_tiles : tile / p.num_n_tiles;
             const int nt = p.m_fastest ? tile / p.num_m_tiles : tile % p.num_n_tiles;
             // global row / validity
             long long grow;
             int batch_idx;
             bool row_ok;
+            const int rt = mt * CTAS + (int)cta_rank;
             if (p.conv) {
                 const int per_img = p.tiles_x * p.tiles_y;
-                const int b = mt / per_img;
-                const int r = mt % per_img;
+                const int b = rt / per_img;
+                const int r = rt % per_img;
                 const int y = (r / p.tiles_x) * p.TH + row_in_tile / p.TW;
                 const int x = (r % p.tiles_x) * p.TW + row_in_tile % p.TW;
-                row_ok = (y < p.H) && (x < p.W);
+                row_ok = (y < p.H) && (x < p.W) && (b < p.nimg);
                 grow = ((long long)b * p.H + y) * p.W + x;
                 batch_idx = b;
             } else {
-                grow = (long long)mt * BM + row_in_tile;
+                grow = (long long)rt * BM + row_in_tile;
                 row_ok = grow < p.M;
                 batch_idx = p.rows_per_batch > 0 ? (int)(grow / p.rows_per_batch) : 0;
             }
@@ -496,16 +521,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) { if (CTAS == 2 && cta_rank != 0) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
 
     tc_fence_before();
     __syncthreads();
+    if (CTAS == 2) cluster_sync_all();     // CTA 0's MMAs read the peer's shared memory: nobody leaves before both are done
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, S::TMEM_COLS);
+        if (CTAS == 2) tmem_dealloc_2sm(tmem_base, S::TMEM_COLS); else tmem_dealloc(tmem_base, S::TMEM_COLS);
     }
 }
 
@@ -577,24 +603,44 @@ extern int g_force_bn;
 extern long long g_desc_override;
 extern long long g_idesc_override;
 
-template <int BN>
+extern int g_gemm_pair;
+
+// CTA-pair (tcgen05 cta_group::2) mode: a 2-CTA cluster computes a 256 x BN tile, each CTA loading only half of the W tile.
+// Halves the shared-memory fill traffic per flop for W; used for the widest tile when there are enough row tiles.
+static int gemm_pair_mode() {
+    if (g_gemm_pair < 0) {
+        const char* e = getenv("SUPIR_B200_GEMM_PAIR");
+        g_gemm_pair = e ? atoi(e) : 1;
+    }
+    return g_gemm_pair;
+}
+// mode 0: never; 1: where it measured faster (profiles/r01_selftest_pair.log) — not the short-K GEGLU GEMMs, whose
+// epilogue-bound pipeline loses more to the pair's coupled accumulator hand-off than the mainloop gains; 2: always
+static int pick_ctas(const GemmKernelParams& p, int bn) {
+    const int mode = gemm_pair_mode();
+    if (mode == 0 || bn != 256 || p.num_m_tiles < 2) return 1;
+    if (mode == 1 && p.act == 2 && p.num_kb < 16) return 1;
+    return 2;
+}
+
+template <int BN, int CTAS>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
                        GemmKernelParams p, cudaStream_t st) {
+    using S = GemmSmem<BN, CTAS>;
     static bool attr_set = false;
     if (!attr_set) {
-        SUPIR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              GemmSmem<BN>::TOTAL));
+        SUPIR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
         attr_set = true;
     }
     p.num_n_tiles = (p.N + BN - 1) / BN;
+    p.nimg = p.conv ? (int)(p.M / ((long long)p.H * p.W)) : 0;
     {
         uint64_t dt = g_desc_override >= 0 ? (uint64_t)g_desc_override
                                            : (((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61));
         p.desc_hi = (uint32_t)(dt >> 32);
         p.desc_lbo = (uint32_t)(dt & 0xFFFFFFFFu);
-        p.idesc = g_idesc_override >= 0 ? (uint32_t)g_idesc_override : umma_idesc_bf16(BM, BN);
+        p.idesc = g_idesc_override >= 0 ? (uint32_t)g_idesc_override : umma_idesc_bf16(BM * CTAS, BN);
     }
-    const int tiles = p.num_m_tiles * p.num_n_tiles;
     {
         // tile order that minimises HBM traffic under a simple L2 model: the CTAs running together (one round) either share
         // a W tile (m-fastest; A is re-streamed once per n-tile unless it fits L2) or share an A tile (n-fastest; W is
@@ -606,8 +652,27 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
         const double t_nfast = a_bytes + (w_bytes <= l2 ? w_bytes : w_bytes * (rounds_m < 1 ? 1 : rounds_m));
         p.m_fastest = t_mfast < t_nfast ? 1 : 0;
     }
-    const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-    gemm_tcgen05_kernel<BN><<<grid, GEMM_THREADS, GemmSmem<BN>::TOTAL, st>>>(tmA, tmB, tmC, tmR, p);
+    p.num_m_tiles = (p.num_m_tiles + CTAS - 1) / CTAS;     // from here on: tiles of 128 * CTAS rows
+    const int tiles = p.num_m_tiles * p.num_n_tiles;
+    const int slots = device_sm_count() / CTAS;
+    const int grid = CTAS * (tiles < slots ? tiles : slots);
+    if (CTAS == 1) {
+        gemm_tcgen05_kernel<BN, CTAS><<<grid, GEMM_THREADS, S::TOTAL, st>>>(tmA, tmB, tmC, tmR, p);
+    } else {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(GEMM_THREADS);
+        cfg.dynamicSmemBytes = S::TOTAL;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CTAS;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        SUPIR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, CTAS>, tmA, tmB, tmC, tmR, p));
+    }
     count_launch();
     SUPIR_CHECK_CUDA(cudaGetLastError());
     return SUPIR_OK;
@@ -615,7 +680,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 
 // choose the N tile: minimise (rounds over the SMs) x (per-tile time). 160 divides every channel count of SUPIR
 // (320..10240) exactly; 256 has the best shared-memory traffic per flop; narrow tiles fill the machine for small M.
-static int pick_bn(int m_tiles, int N, int num_kb, int force_bn) {
+static int pick_bn(const GemmKernelParams& p, int force_bn) {
+    const int m_tiles = p.num_m_tiles, N = p.N, num_kb = p.num_kb;
     if (force_bn == 64 || force_bn == 128 || force_bn == 160 || force_bn == 256) return force_bn;
     const int sms = device_sm_count();
     int best = 128;
@@ -628,7 +694,7 @@ static int pick_bn(int m_tiles, int N, int num_kb, int force_bn) {
         const long long rounds = (tiles + sms - 1) / sms;
         // MMA time of a tile ~ bn * num_kb (narrow tiles are shared-memory bound: 128-wide costs ~1.15x per column, 64-wide ~1.5x);
         // plus a per-tile overhead (pipeline fill + epilogue not hidden on the last tile) of ~6 k-blocks of a 256-wide tile
-        const double per_col = bn == 256 ? 1.0 : (bn == 160 ? 1.2 : (bn == 128 ? 1.42 : 2.0));   // measured (profiles/r01_*perf2*)
+        const double per_col = bn == 256 ? (pick_ctas(p, 256) == 2 ? 0.9 : 1.0) : (bn == 160 ? 1.2 : (bn == 128 ? 1.42 : 2.0));   // measured (profiles/r01_*perf2*)
         const double tile_cost = bn * per_col * num_kb + 256.0 * 6.0;
         const double cost = rounds * tile_cost;
         if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
@@ -637,6 +703,7 @@ static int pick_bn(int m_tiles, int N, int num_kb, int force_bn) {
 }
 
 int g_force_bn = 0;
+int g_gemm_pair = -1;             // CTA-pair (cta_group::2) kernel for the 256-wide tile: 0 never, 1 heuristic, 2 always; -1 = env/default
 long long g_desc_override = -1;   // debug: full 64-bit descriptor template (address bits zero), -1 = default
 long long g_idesc_override = -1;  // debug: instruction descriptor, -1 = default
 
@@ -687,11 +754,12 @@ static int run_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmKernelPa
         const int rc = make_epi_maps(p, &tmC, &tmR);
         if (rc) return rc;
     }
-    const int bn = pick_bn(p.num_m_tiles, p.N, p.num_kb, g_force_bn);
-    if (bn == 256) return launch_gemm<256>(tmA, tmB, tmC, tmR, p, st);
-    if (bn == 160) return launch_gemm<160>(tmA, tmB, tmC, tmR, p, st);
-    if (bn == 128) return launch_gemm<128>(tmA, tmB, tmC, tmR, p, st);
-    return launch_gemm<64>(tmA, tmB, tmC, tmR, p, st);
+    const int bn = pick_bn(p, g_force_bn);
+    if (bn == 256 && pick_ctas(p, bn) == 2) return launch_gemm<256, 2>(tmA, tmB, tmC, tmR, p, st);
+    if (bn == 256) return launch_gemm<256, 1>(tmA, tmB, tmC, tmR, p, st);
+    if (bn == 160) return launch_gemm<160, 1>(tmA, tmB, tmC, tmR, p, st);
+    if (bn == 128) return launch_gemm<128, 1>(tmA, tmB, tmC, tmR, p, st);
+    return launch_gemm<64, 1>(tmA, tmB, tmC, tmR, p, st);
 }
 
 static int fill_epilogue(GemmKernelParams& p, const supir_epilogue* ep, int N) {
@@ -732,6 +800,11 @@ extern "C" int supir_debug_force_direct_epilogue(int on) {
     return SUPIR_OK;
 }
 
+extern "C" int supir_set_gemm_pair_mode(int on) {
+    g_gemm_pair = on < 0 ? 0 : (on > 2 ? 2 : on);
+    return SUPIR_OK;
+}
+
 extern "C" int supir_set_gemm_tile_n(int bn) {
     g_force_bn = bn;
     return SUPIR_OK;
@@ -752,7 +825,7 @@ extern "C" int supir_gemm_bf16(const void* A, long long lda, const void* W, long
     if (rc) return rc;
     SUPIR_REQUIRE(ldc >= p.n_out, "supir_gemm_bf16: ldc %lld < output columns %d", ldc, p.n_out);
     p.out = out; p.ldc = ldc;
-    const int bn = pick_bn(p.num_m_tiles, N, p.num_kb, g_force_bn);
+    const int bn = pick_bn(p, g_force_bn);
     CUtensorMap tmA, tmB;
     {
         const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
@@ -764,7 +837,7 @@ extern "C" int supir_gemm_bf16(const void* A, long long lda, const void* W, long
     {
         const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
         const uint64_t str[1] = {(uint64_t)ldw};
-        const uint32_t box[2] = {BK, (uint32_t)bn};
+        const uint32_t box[2] = {BK, (uint32_t)(bn / pick_ctas(p, bn))};
         rc = make_tmap_bf16(&tmB, W, 2, dims, str, box);
         if (rc) return rc;
     }
@@ -801,7 +874,7 @@ extern "C" int supir_conv3x3_bf16(const void* x, long long ldx, const void* Wp, 
     if (rc) return rc;
     SUPIR_REQUIRE(ldc >= p.n_out, "supir_conv3x3_bf16: ldc %lld < output columns %d", ldc, p.n_out);
     p.out = out; p.ldc = ldc;
-    const int bn = pick_bn(p.num_m_tiles, Cout, p.num_kb, g_force_bn);
+    const int bn = pick_bn(p, g_force_bn);
     CUtensorMap tmA, tmB;
     {
         const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Wd, (uint64_t)H, (uint64_t)B};
@@ -813,7 +886,7 @@ extern "C" int supir_conv3x3_bf16(const void* x, long long ldx, const void* Wp, 
     {
         const uint64_t dims[2] = {(uint64_t)(9 * Cin), (uint64_t)Cout};
         const uint64_t str[1] = {(uint64_t)(9 * Cin)};
-        const uint32_t box[2] = {BK, (uint32_t)bn};
+        const uint32_t box[2] = {BK, (uint32_t)(bn / pick_ctas(p, bn))};
         rc = make_tmap_bf16(&tmB, Wp, 2, dims, str, box);
         if (rc) return rc;
     }

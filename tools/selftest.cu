@@ -506,6 +506,38 @@ int main(int argc, char** argv) {
         test_conv(1, 150, 150, 128, 128, 20000, false, false);
         test_conv(2, 8, 8, 128, 256, 0, false, false);
     }
+    if (what == "pair" || what == "all") {   // CTA-pair (cta_group::2) kernel: correctness, then speed against the 1-CTA kernel
+        supir_set_gemm_pair_mode(2);
+        supir_set_gemm_tile_n(256);
+        test_gemm(256, 256, 64, 0, false, false, false, 0, false, true);
+        test_gemm(256, 256, 256, 0, true, false, false, 0);
+        test_gemm(300, 200, 192, 0, true, true, false, 0);
+        test_gemm(1000, 328, 320, 1, true, false, true, 0);
+        test_gemm(2048, 2560, 1280, 2, true, true, false, 20000);
+        test_gemm(20000, 640, 640, 0, true, true, false, 20000);
+        test_gemm(40000, 1280, 320, 0, true, true, false, 20000);
+        test_conv(2, 32, 32, 64, 128, 0, true, true);
+        test_conv(1, 17, 23, 72, 40, 0, false, false);
+        test_conv(3, 24, 24, 320, 320, 20000, true, true);     // odd patch count: the last pair has a padding CTA
+        test_conv(2, 64, 64, 320, 320, 20000, true, true);
+        supir_set_gemm_tile_n(0);
+        struct Sh { int M, N, K, act; } shapes[] = {{14336, 10240, 1280, 2}, {14336, 1280, 1280, 0}, {57344, 640, 640, 0},
+                                                    {57344, 5120, 640, 2}, {14336, 1280, 5120, 0}, {8192, 8192, 8192, 0}};
+        for (auto& sh : shapes)
+            for (int pm : {0, 2}) {
+                supir_set_gemm_pair_mode(pm);
+                printf("pair=%d ", pm);
+                perf_gemm(sh.M, sh.N, sh.K, sh.act, 256);
+            }
+        for (int pm : {0, 2}) {
+            supir_set_gemm_pair_mode(pm);
+            printf("pair=%d ", pm);
+            perf_conv(14, 32, 32, 1280, 1280, 256);
+            printf("pair=%d ", pm);
+            perf_conv(14, 64, 64, 640, 640, 256);
+        }
+        supir_set_gemm_pair_mode(1);
+    }
     if (what == "attn" || what == "all") {
         test_attention(1, 1, 128, 128, 0);
         test_attention(1, 2, 128, 256, 0);
