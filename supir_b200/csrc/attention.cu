@@ -10,10 +10,12 @@
 //   warp 1 lane 0 : tcgen05.mma issuer. Per tile X and key block j:
 //                     S_X = Q_X K_j^T   (128x128x64, TMEM, overwritten every block)
 //                     O_X += P_X V_j    (128x64x128, ACCUMULATED in TMEM across blocks)
-//                   with V consumed in its natural [kv, d] layout as an MN-major B operand.
+//                   with P_X read straight from TENSOR MEMORY (A-in-TMEM form of tcgen05.mma: P never touches shared
+//                   memory, whose bandwidth the QK/PV operand reads already saturate) and V consumed in its natural
+//                   [kv, d] layout as an MN-major B operand.
 //   warps 4..7    : softmax group of tile A, warps 8..11: tile B — one query row per thread. The whole S row (128 fp32) is
-//                   read from TMEM once into registers; p = ex2((s - m) * scale) goes to shared memory as the bf16 K-major
-//                   128B-swizzled A operand of the PV MMA.
+//                   read from TMEM once into registers; p = ex2((s - m) * scale) is packed to bf16 pairs and stored back to
+//                   TMEM (tcgen05.st, 64 columns per tile) as the A operand of the PV MMA.
 // Online softmax without touching O every block: the exponent reference m is only moved when the running row maximum
 // exceeds it by more than 8 (p <= 2^8 stays exact enough in bf16/fp32); only then the warp rescales its 32 rows of O in
 // TMEM (tcgen05.ld / tcgen05.st) and its row sum. Two independent tiles keep the tensor pipe and the MUFU pipe busy
@@ -29,7 +31,7 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* d
 static constexpr int ATT_BM = 128;   // queries per tile (two tiles per CTA)
 static constexpr int ATT_BN = 128;   // keys per block
 static constexpr int ATT_D = 64;
-static constexpr int ATT_STAGES = 3;
+static constexpr int ATT_STAGES = 4;
 static constexpr int ATT_THREADS = 384;   // warpgroup 0: TMA + MMA (+2 idle warps), warpgroups 1/2: softmax of tile A/B
 static constexpr float ATT_RESCALE_THRESHOLD = 8.0f;   // log2 units
 
@@ -47,12 +49,10 @@ struct AttnSmem {
     static constexpr int Q_BYTES = ATT_BM * ATT_D * 2;          // 16 KB per tile
     static constexpr int K_BYTES = ATT_BN * ATT_D * 2;          // 16 KB
     static constexpr int V_BYTES = ATT_BN * ATT_D * 2;          // 16 KB
-    static constexpr int P_BYTES = ATT_BM * ATT_BN * 2;         // 32 KB per tile (two 64-column halves)
     static constexpr int OFF_Q = 0;
     static constexpr int OFF_K = OFF_Q + 2 * Q_BYTES;
     static constexpr int OFF_V = OFF_K + ATT_STAGES * K_BYTES;
-    static constexpr int OFF_P = OFF_V + ATT_STAGES * V_BYTES;
-    static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
+    static constexpr int OFF_BAR = OFF_V + ATT_STAGES * V_BYTES;
     static constexpr int TOTAL = OFF_BAR + 256 + 1024;
 };
 
@@ -64,15 +64,14 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     uint8_t* sQ = smem + AttnSmem::OFF_Q;
     uint8_t* sK = smem + AttnSmem::OFF_K;
     uint8_t* sV = smem + AttnSmem::OFF_V;
-    uint8_t* sP = smem + AttnSmem::OFF_P;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnSmem::OFF_BAR);
     uint64_t* q_full = bars;                // 1
-    uint64_t* kv_full = bars + 1;           // [3]
-    uint64_t* kv_empty = bars + 4;          // [3]
-    uint64_t* s_full = bars + 7;            // [2] per tile
-    uint64_t* p_full = bars + 9;            // [2] per tile
-    uint64_t* pv_done = bars + 11;          // [2] per tile
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
+    uint64_t* kv_full = bars + 1;                       // [ATT_STAGES]
+    uint64_t* kv_empty = kv_full + ATT_STAGES;          // [ATT_STAGES]
+    uint64_t* s_full = kv_empty + ATT_STAGES;           // [2] per tile
+    uint64_t* p_full = s_full + 2;                      // [2] per tile
+    uint64_t* pv_done = p_full + 2;                     // [2] per tile
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qblk = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
@@ -101,7 +100,7 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
-    // TMEM columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384)
+    // TMEM columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512) (bf16 pairs)
 
     if (warp < 4) {
       asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -151,16 +150,13 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     mbar_wait(&p_full[x], j & 1);       // P_X(j) written, S_X(j) consumed
                     tc_fence_after();
                     if (j + 1 < nblk) issue_qk(x, nstage);
-                    const uint32_t pbase = smem_u32(sP + x * AttnSmem::P_BYTES);
                     const uint32_t vbase = smem_u32(sV + stage * AttnSmem::V_BYTES);
 #pragma unroll
                     for (int k = 0; k < ATT_BN / 16; ++k) {
-                        // A = P: K-major, two 64-column halves of 16 KB, 32 B per 16-k step inside a half
-                        const uint32_t pa = pbase + (k >> 2) * (AttnSmem::P_BYTES / 2) + (k & 3) * 32;
-                        // B = V: MN-major (d contiguous), 16 kv rows of 128 B per step
+                        // A = P in TMEM: 16 k-elements = 8 columns per step; B = V: MN-major (d contiguous), 16 kv rows of 128 B
                         const uint32_t va = vbase + k * 16 * 128;
-                        umma_bf16(tmem_base + 256 + x * ATT_D, dtemplate | ((pa >> 4) & 0x3FFF),
-                                  dtemplate | ((va >> 4) & 0x3FFF), p.idesc_pv, (j | k) != 0);
+                        umma_bf16_ts(tmem_base + 256 + x * ATT_D, tmem_base + 384 + x * 64 + k * 8,
+                                     dtemplate | ((va >> 4) & 0x3FFF), p.idesc_pv, (j | k) != 0);
                     }
                     umma_commit(&pv_done[x]);
                 }
@@ -180,7 +176,7 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
             const uint32_t tS = tmem_base + x * ATT_BN + lane_off;
             const uint32_t tO = tmem_base + 256 + x * ATT_D + lane_off;
-            uint8_t* p_row = sP + x * AttnSmem::P_BYTES + row * 128;
+            const uint32_t tP = tmem_base + 384 + x * 64 + lane_off;
             float m_ref = 0.f, l_run = 0.f;
             for (int j = 0; j < nblk; ++j) {
                 mbar_wait(&s_full[x], j & 1);
@@ -238,28 +234,24 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
                 for (int t = 0; t < 8; ++t) ls[t] = 0.f;
 #pragma unroll
-                for (int c0 = 0; c0 < ATT_BN; c0 += 32) {
-                    uint8_t* half_base = p_row + (c0 >> 6) * (AttnSmem::P_BYTES / 2);
+                for (int c0 = 0; c0 < ATT_BN; c0 += 64) {
+                    uint32_t pk[32];                                     // 64 probabilities as bf16 pairs
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int i = 0; i < 64; i += 8) {
                         float e[8];
 #pragma unroll
                         for (int t = 0; t < 8; ++t) {
-                            e[t] = ex2_approx(fmaf(__uint_as_float(s[c0 + q * 8 + t]), p.scale_log2, -m_ref));
+                            e[t] = ex2_approx(fmaf(__uint_as_float(s[c0 + i + t]), p.scale_log2, -m_ref));
                             ls[t] += e[t];
                         }
-                        const int chunk = ((c0 & 63) >> 3) + q;         // 16-byte chunk index inside the 128-byte row
-                        uint4 u;
-                        u.x = pack_bf16x2(e[0], e[1]);
-                        u.y = pack_bf16x2(e[2], e[3]);
-                        u.z = pack_bf16x2(e[4], e[5]);
-                        u.w = pack_bf16x2(e[6], e[7]);
-                        *reinterpret_cast<uint4*>(half_base + ((chunk ^ (row & 7)) << 4)) = u;
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) pk[(i >> 1) + t] = pack_bf16x2(e[2 * t], e[2 * t + 1]);
                     }
+                    tmem_st_32x32(tP + (c0 >> 1), pk);
                 }
+                tmem_st_wait();
                 l_run += ((ls[0] + ls[1]) + (ls[2] + ls[3])) + ((ls[4] + ls[5]) + (ls[6] + ls[7]));
                 tc_fence_before();
-                fence_proxy_async_smem();   // generic-proxy writes of P -> visible to the tensor-core (async) proxy
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&p_full[x]);
             }
