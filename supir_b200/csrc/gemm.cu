@@ -61,7 +61,7 @@ struct GemmSmem {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = (BN / CTAS) * BK * 2;   // a CTA pair splits the B tile
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = CTAS == 2 ? 4 : ((BN == 256) ? 3 : (BN == 160 ? 4 : (BN == 128 ? 4 : 6)));
+    static constexpr int STAGES = CTAS == 2 ? (BN == 256 ? 4 : 6) : ((BN == 256) ? 3 : (BN == 160 ? 4 : (BN == 128 ? 4 : 6)));
     // epilogue staging: per half-group (4 warps = 128 rows) two 8 KB output buffers and two 8 KB residual buffers
     // (128 rows x 32 bf16 columns, 64B-swizzled), plus the tile's bias (+ per-image vector) for both accumulators
     static constexpr int CH_BYTES = BM * 32 * 2;
@@ -618,8 +618,12 @@ static int gemm_pair_mode() {
 // epilogue-bound pipeline loses more to the pair's coupled accumulator hand-off than the mainloop gains; 2: always
 static int pick_ctas(const GemmKernelParams& p, int bn) {
     const int mode = gemm_pair_mode();
-    if (mode == 0 || bn != 256 || p.num_m_tiles < 2) return 1;
-    if (mode == 1 && p.act == 2 && p.num_kb < 16) return 1;
+    if (mode == 0 || bn < 128 || p.num_m_tiles < 2) return 1;
+    if (mode == 1) {
+        if (p.act == 2 && p.num_kb < 16) return 1;
+        // the narrower tiles only gain from pairing when the mainloop is long (K >= 4096) and hurt below that
+        if (bn < 256 && (p.conv || p.num_kb < 64)) return 1;
+    }
     return 2;
 }
 
@@ -755,7 +759,11 @@ static int run_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmKernelPa
         if (rc) return rc;
     }
     const int bn = pick_bn(p, g_force_bn);
-    if (bn == 256 && pick_ctas(p, bn) == 2) return launch_gemm<256, 2>(tmA, tmB, tmC, tmR, p, st);
+    if (pick_ctas(p, bn) == 2) {
+        if (bn == 256) return launch_gemm<256, 2>(tmA, tmB, tmC, tmR, p, st);
+        if (bn == 160) return launch_gemm<160, 2>(tmA, tmB, tmC, tmR, p, st);
+        return launch_gemm<128, 2>(tmA, tmB, tmC, tmR, p, st);
+    }
     if (bn == 256) return launch_gemm<256, 1>(tmA, tmB, tmC, tmR, p, st);
     if (bn == 160) return launch_gemm<160, 1>(tmA, tmB, tmC, tmR, p, st);
     if (bn == 128) return launch_gemm<128, 1>(tmA, tmB, tmC, tmR, p, st);

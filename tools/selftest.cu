@@ -520,14 +520,33 @@ int main(int argc, char** argv) {
         test_conv(1, 17, 23, 72, 40, 0, false, false);
         test_conv(3, 24, 24, 320, 320, 20000, true, true);     // odd patch count: the last pair has a padding CTA
         test_conv(2, 64, 64, 320, 320, 20000, true, true);
+        for (int bn : {160, 128}) {
+            supir_set_gemm_tile_n(bn);
+            test_gemm(256, 256, 256, 0, true, false, false, 0);
+            test_gemm(300, 200, 192, 0, true, true, false, 0);
+            test_gemm(1000, 328, 320, 1, true, false, true, 0);
+            test_gemm(2048, 2560, 1280, 2, true, true, false, 20000);
+            test_gemm(20000, 640, 640, 0, true, true, false, 20000);
+            test_conv(3, 24, 24, 320, 320, 20000, true, true);
+        }
         supir_set_gemm_tile_n(0);
         struct Sh { int M, N, K, act; } shapes[] = {{14336, 10240, 1280, 2}, {14336, 1280, 1280, 0}, {57344, 640, 640, 0},
-                                                    {57344, 5120, 640, 2}, {14336, 1280, 5120, 0}, {8192, 8192, 8192, 0}};
+                                                    {57344, 5120, 640, 2}, {57344, 1920, 640, 0}, {57344, 640, 2560, 0},
+                                                    {229376, 320, 320, 0}, {14336, 1280, 5120, 0}, {8192, 8192, 8192, 0}};
         for (auto& sh : shapes)
+            for (int bn : {256, 160, 128})
+                for (int pm : {0, 2}) {
+                    supir_set_gemm_pair_mode(pm);
+                    printf("pair=%d ", pm);
+                    perf_gemm(sh.M, sh.N, sh.K, sh.act, bn);
+                }
+        for (int bn : {160, 128})
             for (int pm : {0, 2}) {
                 supir_set_gemm_pair_mode(pm);
                 printf("pair=%d ", pm);
-                perf_gemm(sh.M, sh.N, sh.K, sh.act, 256);
+                perf_conv(14, 128, 128, 320, 320, bn);
+                printf("pair=%d ", pm);
+                perf_conv(14, 64, 64, 640, 640, bn);
             }
         for (int pm : {0, 2}) {
             supir_set_gemm_pair_mode(pm);
