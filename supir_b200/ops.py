@@ -255,8 +255,11 @@ def timestep_embedding(t, out):
 def linear_small_m(x, w, bias, out, silu_in=False, silu_out=False, add=None):
     _need_cuda(x, w, out)
     assert x.dtype == torch.float32 and out.dtype == torch.float32 and w.dtype == BF16 and w.is_contiguous()
-    call("supir_linear_small_m", _ptr(x), x.stride(0), _ptr(w), _ptr(bias), _ptr(out), out.stride(0), x.shape[0], w.shape[0],
-         w.shape[1], int(silu_in), int(silu_out), _ptr(add), 0 if add is None else add.stride(0), _stream())
+    for r0 in range(0, x.shape[0], 16):     # the kernel keeps <= 16 rows in registers; larger batches go in slices
+        xs, os_ = x[r0:r0 + 16], out[r0:r0 + 16]
+        ad = None if add is None else add[r0:r0 + 16]
+        call("supir_linear_small_m", _ptr(xs), x.stride(0), _ptr(w), _ptr(bias), _ptr(os_), out.stride(0), xs.shape[0], w.shape[0],
+             w.shape[1], int(silu_in), int(silu_out), _ptr(ad), 0 if ad is None else add.stride(0), _stream())
     return out
 
 
