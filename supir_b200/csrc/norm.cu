@@ -75,15 +75,33 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long l
     __syncthreads();
     if (is_last) {
         __threadfence();
-        for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        // block partials -> final sums, in a fixed order: `lanes` threads per group each add every lanes-th partial in block
+        // order, then the lanes' subtotals are added in lane order (deterministic, and not a serial walk over all blocks)
+        double* red = reinterpret_cast<double*>(sm);            // [blockDim.x][2], fits: 2*kp*C floats >= 4*blockDim.x
+        int lanes = blockDim.x / G;
+        if (lanes < 1) lanes = 1;
+        const int gpp = blockDim.x / lanes;                     // groups handled per pass
+        const int l = threadIdx.x % lanes;
+        for (int g0 = 0; g0 < G; g0 += gpp) {
+            const int g = g0 + threadIdx.x / lanes;
             double a = 0, q = 0;
-            for (int k = 0; k < nblk; ++k) {
-                const double* src = partial + (((long long)b * nblk + k) * G + g) * 2;
-                a += __ldcg(src);
-                q += __ldcg(src + 1);
+            if (g < G && threadIdx.x < gpp * lanes) {
+                for (int k = l; k < nblk; k += lanes) {
+                    const double* src = partial + (((long long)b * nblk + k) * G + g) * 2;
+                    a += __ldcg(src);
+                    q += __ldcg(src + 1);
+                }
             }
-            sums[((long long)b * G + g) * 2] = a;
-            sums[((long long)b * G + g) * 2 + 1] = q;
+            __syncthreads();
+            red[2 * threadIdx.x] = a;
+            red[2 * threadIdx.x + 1] = q;
+            __syncthreads();
+            if (g < G && l == 0 && threadIdx.x < gpp * lanes) {
+                double ta = 0, tq = 0;
+                for (int i = 0; i < lanes; ++i) { ta += red[2 * (threadIdx.x + i)]; tq += red[2 * (threadIdx.x + i) + 1]; }
+                sums[((long long)b * G + g) * 2] = ta;
+                sums[((long long)b * G + g) * 2 + 1] = tq;
+            }
         }
     }
 }
@@ -280,37 +298,76 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long 
     }
 }
 
-// row softmax for the materialised single-head VAE attention: P = softmax(S * scale), fp32 in, bf16 out
+// row softmax for the materialised single-head VAE attention: P = softmax(S * scale), fp32 in, bf16 out.
+// One block per row; the row is read from HBM once (128-bit loads) into shared memory, exponentiated in place, and written
+// once as bf16 (the generic kernel below re-reads the row from global memory and serves rows that do not fit or align).
+__device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
+    v = is_max ? warp_max(v) : warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : (is_max ? -INFINITY : 0.f);
+        t = is_max ? warp_max(t) : warp_sum(t);
+        if (threadIdx.x == 0) red[32] = t;
+    }
+    __syncthreads();
+    return red[32];
+}
+
+__global__ void softmax_rows_smem_kernel(const float* __restrict__ S, long long lds, __nv_bfloat16* __restrict__ P,
+                                         long long ldp, int cols, float scale) {
+    extern __shared__ float rowbuf[];      // cols rounded up to 8
+    __shared__ float red[33];
+    const long long row = blockIdx.x;
+    const float4* s4 = reinterpret_cast<const float4*>(S + row * lds);
+    const int n4 = cols >> 2;
+    float m = -INFINITY;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+        const float4 v = __ldcs(s4 + i);
+        reinterpret_cast<float4*>(rowbuf)[i] = v;
+        m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+    }
+    for (int c = (n4 << 2) + threadIdx.x; c < cols; c += blockDim.x) {
+        const float v = S[row * lds + c];
+        rowbuf[c] = v;
+        m = fmaxf(m, v);
+    }
+    m = block_reduce(m, red, true);
+    float sum = 0.f;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+        const float e = __expf((rowbuf[c] - m) * scale);
+        rowbuf[c] = e;
+        sum += e;
+    }
+    sum = block_reduce(sum, red, false);
+    const float inv = 1.f / sum;
+    __nv_bfloat16* p = P + row * ldp;
+    const int n8 = cols >> 3;
+    for (int i = threadIdx.x; i < n8; i += blockDim.x) {
+        const float4 a = reinterpret_cast<const float4*>(rowbuf)[2 * i], c = reinterpret_cast<const float4*>(rowbuf)[2 * i + 1];
+        uint4 u;
+        u.x = pack_bf16x2(a.x * inv, a.y * inv);
+        u.y = pack_bf16x2(a.z * inv, a.w * inv);
+        u.z = pack_bf16x2(c.x * inv, c.y * inv);
+        u.w = pack_bf16x2(c.z * inv, c.w * inv);
+        reinterpret_cast<uint4*>(p)[i] = u;
+    }
+    for (int c = (n8 << 3) + threadIdx.x; c < cols; c += blockDim.x) p[c] = __float2bfloat16_rn(rowbuf[c] * inv);
+}
+
 __global__ void softmax_rows_kernel(const float* __restrict__ S, long long lds, __nv_bfloat16* __restrict__ P,
                                     long long ldp, int cols, float scale) {
     const long long row = blockIdx.x;
     const float* s = S + row * lds;
-    __shared__ float red[32];
+    __shared__ float red[33];
     float m = -INFINITY;
     for (int c = threadIdx.x; c < cols; c += blockDim.x) m = fmaxf(m, s[c]);
-    m = warp_max(m);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -INFINITY;
-        t = warp_max(t);
-        if (threadIdx.x == 0) red[0] = t;
-    }
-    __syncthreads();
-    m = red[0];
-    __syncthreads();
+    m = block_reduce(m, red, true);
     float sum = 0.f;
     for (int c = threadIdx.x; c < cols; c += blockDim.x) sum += __expf((s[c] - m) * scale);
-    sum = warp_sum(sum);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
-        t = warp_sum(t);
-        if (threadIdx.x == 0) red[0] = t;
-    }
-    __syncthreads();
-    const float inv = 1.f / red[0];
+    sum = block_reduce(sum, red, false);
+    const float inv = 1.f / sum;
     __nv_bfloat16* p = P + row * ldp;
     for (int c = threadIdx.x; c < cols; c += blockDim.x) p[c] = __float2bfloat16_rn(__expf((s[c] - m) * scale) * inv);
 }
@@ -323,6 +380,10 @@ static int gn_launch_shape(int HW, int C, int& threads, int& ppb, int& blocks_x)
     // enough blocks to cover the machine a few times, but at least 32 pixels per thread-row to amortise the reduction
     ppb = kp * 16;
     if (ppb < 64) ppb = 64;
+    // very large images (tiled VAE): at most ~592 blocks per image (4 per SM). Depends on (HW, C) only, never on the batch:
+    // a window-sharded run must add in the same order as the unsharded one.
+    const int cap = (HW + 591) / 592;
+    if (ppb < cap) ppb = (cap + kp - 1) / kp * kp;
     blocks_x = (HW + ppb - 1) / ppb;
     return 0;
 }
@@ -439,8 +500,20 @@ extern "C" int supir_layernorm_bf16(const void* x, long long ldx, void* y, long 
 extern "C" int supir_softmax_rows(const float* S, long long lds, void* P, long long ldp, long long rows, int cols,
                                   float scale, void* stream) {
     SUPIR_REQUIRE(S && P && rows > 0 && cols > 0, "supir_softmax_rows: bad args");
-    softmax_rows_kernel<<<(unsigned)rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        S, lds, reinterpret_cast<__nv_bfloat16*>(P), ldp, cols, scale);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t smem = (size_t)((cols + 7) / 8 * 8) * sizeof(float);
+    const bool aligned = (lds % 4 == 0) && (ldp % 8 == 0) && (reinterpret_cast<uintptr_t>(S) % 16 == 0) &&
+                         (reinterpret_cast<uintptr_t>(P) % 16 == 0);
+    if (aligned && cols >= 1024 && smem <= 200 * 1024) {
+        static size_t max_set = 0;
+        if (smem > 48 * 1024 && smem > max_set) {
+            SUPIR_CHECK_CUDA(cudaFuncSetAttribute(softmax_rows_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            max_set = smem;
+        }
+        softmax_rows_smem_kernel<<<(unsigned)rows, 1024, smem, st>>>(S, lds, reinterpret_cast<__nv_bfloat16*>(P), ldp, cols, scale);
+    } else {
+        softmax_rows_kernel<<<(unsigned)rows, 256, 0, st>>>(S, lds, reinterpret_cast<__nv_bfloat16*>(P), ldp, cols, scale);
+    }
     count_launch();
     SUPIR_CHECK_CUDA(cudaGetLastError());
     return SUPIR_OK;
