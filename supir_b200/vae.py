@@ -135,18 +135,20 @@ class _VAENet(nn.Module):
         return self
 
     # ---- step execution on one tile (in place on the tile record) ----
-    def _apply_step(self, pool, step, tile):
+    def _apply_step(self, pool, step, tile, add_res=False):
+        """`add_res`: the step is followed by the block's skip connection, folded into this step's GEMM epilogue."""
         kind = step[0]
         a: Act = tile["h"]
         if kind == "conv":
             out = pool.get((a.rows, step[3]))
-            ops.conv3x3(a.t, a.B, a.H, a.W, step[1], out, bias=step[2])
-            pool.put(a.t)
+            r = tile["res"].pop() if add_res else None
+            ops.conv3x3(a.t, a.B, a.H, a.W, step[1], out, bias=step[2], residual=r)
+            pool.put(a.t, r)
             tile["h"] = Act(out, a.B, a.H, a.W)
         elif kind == "store_res":
             if step[1] is None:
-                r = pool.get((a.rows, a.C))
-                ops.copy2d(a.t, r)
+                r = a.t                     # identity skip: hold the tensor itself; the norm that follows must not recycle it
+                tile["keep"] = r
             else:
                 r = pool.get((a.rows, step[3]))
                 ops.gemm(a.t, step[1], r, bias=step[2])
@@ -174,11 +176,11 @@ class _VAENet(nn.Module):
             pool.put(cols, a.t)
             tile["h"] = Act(out, a.B, Ho, Wo)
         elif kind == "attn":
-            self._attn(pool, step, tile)
+            self._attn(pool, step, tile, add_res)
         else:
             raise ValueError(kind)
 
-    def _attn(self, pool, step, tile):
+    def _attn(self, pool, step, tile, add_res=False):
         """softmax(q k^T c^-0.5) v with one 512-wide head: two tensor-core GEMMs around a row-softmax kernel; the score
         matrix is materialised in HBM (fp32) — memory is not the constraint on a 180 GB part, and it is < 2 % of the VAE."""
         _, wqk, bqk, wv, bv, wo, bo, C = step
@@ -186,6 +188,7 @@ class _VAENet(nn.Module):
         L = a.HW
         Lp = (L + 7) // 8 * 8
         out = pool.get((a.rows, C))
+        r = tile["res"].pop() if add_res else None
         for b in range(a.B):
             x = a.t[b * L:(b + 1) * L]
             qk = pool.get((L, 2 * C))
@@ -200,16 +203,19 @@ class _VAENet(nn.Module):
             o = pool.get((L, C))
             # softmax rows sum to one, so the value bias can be added after the product: (P (V + 1 b^T)) = P V + 1 b^T
             ops.gemm(P[:, :L], vT[:, :L], o, bias=bv)
-            ops.gemm(o, wo, out[b * L:(b + 1) * L], bias=bo)
+            ops.gemm(o, wo, out[b * L:(b + 1) * L], bias=bo, residual=None if r is None else r[b * L:(b + 1) * L])
             pool.put(qk, vT, S, P, o)
-        pool.put(a.t)
+        pool.put(a.t, r)
         tile["h"] = Act(out, a.B, a.H, a.W)
 
     def _norm_apply(self, pool, step, tile, sums=None, mean=None, var=None):
         a: Act = tile["h"]
         out = pool.get((a.rows, a.C))
         ops.groupnorm_apply(a.t, a.B, a.HW, out, step[1], step[2], 1e-6, tile.get("fuse_silu", False), sums=sums, mean=mean, var=var)
-        pool.put(a.t)
+        if tile.get("keep") is a.t:
+            tile["keep"] = None             # held as a skip connection (see store_res)
+        else:
+            pool.put(a.t)
         tile["h"] = Act(out, a.B, a.H, a.W)
 
     # ---- drivers ----
@@ -246,10 +252,12 @@ class _VAENet(nn.Module):
         pool.put(a.t)
 
     def _fused_steps(self):
-        """(step, fuse_silu) pairs: a 'silu' right after a 'norm' is folded into the norm-apply kernel."""
+        """(step, fused) pairs: a 'silu' right after a 'norm' is folded into the norm-apply kernel, and an 'add_res' right
+        after a conv / attention into that step's GEMM epilogue (`fused` is True for the absorbing step)."""
         steps, out, i = self._steps, [], 0
         while i < len(steps):
-            if steps[i][0] == "norm" and i + 1 < len(steps) and steps[i + 1][0] == "silu":
+            nxt = steps[i + 1][0] if i + 1 < len(steps) else None
+            if (steps[i][0] == "norm" and nxt == "silu") or (steps[i][0] in ("conv", "attn") and nxt == "add_res"):
                 out.append((steps[i], True))
                 i += 2
             else:
@@ -274,7 +282,7 @@ class _VAENet(nn.Module):
                 self._norm_apply(pool, step, tile, sums=ws)
                 pool.put(ws)
             else:
-                self._apply_step(pool, step, tile)
+                self._apply_step(pool, step, tile, fuse)
         a = tile["h"]
         out = torch.empty((a.B, self._conv_out[2], a.H, a.W), dtype=torch.float32, device=x.device)
         self._finish_tile(pool, tile, out)
@@ -303,7 +311,7 @@ class _VAENet(nn.Module):
         for step, fuse in self._fused_steps():
             if step[0] != "norm":
                 for i in mine:
-                    self._apply_step(pool, step, tiles[i])
+                    self._apply_step(pool, step, tiles[i], fuse)
                 if step[0] == "upsample":
                     dims = [(2 * h, 2 * w) for h, w in dims]
                 elif step[0] == "downsample":
