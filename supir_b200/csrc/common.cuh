@@ -74,7 +74,7 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
     return __bfloat1622float2(t);
 }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 // erf-form GELU — F.gelu default used by GEGLU (reference sgm/modules/attention.py:91):  gelu(g) = g/2 + |g|/2 * erf(|g|/sqrt2).
 // erf via Abramowitz-Stegun 7.1.26 (abs err <= 1.5e-7, far below the bf16 rounding of the result) with 1/sqrt2 folded
 // into the constants: 2 MUFU (rcp, ex2) + 7 FFMA + 4 FMUL, branch-free. libdevice erff (~40 instructions with a slow

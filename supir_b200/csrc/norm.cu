@@ -133,53 +133,77 @@ __global__ void gn_merge_tiles_kernel(const float* __restrict__ tile_mean, const
     var[i] = v;
 }
 
-// y = (x - mean) * rsqrt(var + eps) * gamma + beta [-> SiLU] ; bf16 in, bf16 out, channels-last
+// Per-thread scale / shift of one 8-channel vector: y = x * sc + sh with sc = rstd * gamma, sh = beta - mean * sc.
+// Statistics come either as fp64 (sum, sumsq) pairs or as fp32 (mean, biased var).
+__device__ __forceinline__ void gn_scale_shift(int b, int c0, int C, int G, const double* __restrict__ sums, double count,
+                                               const float* __restrict__ mean, const float* __restrict__ var,
+                                               const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                               float (&sc)[8], float (&sh)[8]) {
+    const int cpg = C / G;
+    int g_prev = -1;
+    float m = 0.f, rstd = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        const int g = c / cpg;
+        if (g != g_prev) {
+            float v;
+            if (sums) {
+                const double dm = sums[((long long)b * G + g) * 2] / count;
+                double dv = sums[((long long)b * G + g) * 2 + 1] / count - dm * dm;
+                if (dv < 0) dv = 0;
+                m = (float)dm; v = (float)dv;
+            } else {
+                m = mean[b * G + g]; v = var[b * G + g];
+            }
+            rstd = rsqrtf(v + eps);
+            g_prev = g;
+        }
+        sc[j] = rstd * (gamma ? gamma[c] : 1.f);
+        sh[j] = (beta ? beta[c] : 0.f) - m * sc[j];
+    }
+}
+
+// y = (x - mean) * rsqrt(var + eps) * gamma + beta [-> SiLU] ; bf16 in, bf16 out, channels-last.
+// block = kp pixel lanes x (C/8) channel vectors; a thread keeps its vector's scale / shift in registers and walks pixels.
 __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y,
                                 long long ldy, int HW, int C, int G, const float* __restrict__ mean,
                                 const float* __restrict__ var, const double* __restrict__ sums, double count,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
                                 int pixels_per_block) {
-    extern __shared__ float sm[];  // scale[C], shift[C]
-    const int b = blockIdx.y;
-    const int cpg = C / G;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const int g = c / cpg;
-        float m, v;
-        if (sums) {
-            const double dm = sums[((long long)b * G + g) * 2] / count;
-            double dv = sums[((long long)b * G + g) * 2 + 1] / count - dm * dm;
-            if (dv < 0) dv = 0;
-            m = (float)dm; v = (float)dv;
-        } else {
-            m = mean[b * G + g]; v = var[b * G + g];
-        }
-        const float rstd = rsqrtf(v + eps);
-        const float sc = rstd * (gamma ? gamma[c] : 1.f);
-        sm[c] = sc;
-        sm[C + c] = (beta ? beta[c] : 0.f) - m * sc;
-    }
-    __syncthreads();
     const int cv_count = C >> 3;
+    const int kp = blockDim.x / cv_count;
+    const int cv = threadIdx.x % cv_count;
+    const int pl = threadIdx.x / cv_count;
+    const int b = blockIdx.y;
+    float sc[8], sh[8];
+    gn_scale_shift(b, cv * 8, C, G, sums, count, mean, var, gamma, beta, eps, sc, sh);
     const int p0 = blockIdx.x * pixels_per_block;
     const int p1 = min(p0 + pixels_per_block, HW);
-    const long long total = (long long)(p1 - p0) * cv_count;
-    for (long long i = threadIdx.x; i < total; i += blockDim.x) {
-        const int p = p0 + (int)(i / cv_count);
-        const int cv = (int)(i % cv_count);
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + ((long long)b * HW + p) * ldx + cv * 8));
+    const __nv_bfloat16* xb = x + ((long long)b * HW) * ldx + cv * 8;
+    __nv_bfloat16* yb = y + ((long long)b * HW) * ldy + cv * 8;
+    auto one = [&](const uint4 u, long long p) {
         const uint32_t w[4] = {u.x, u.y, u.z, u.w};
         uint32_t o[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             const float2 f = unpack_bf16x2(w[t]);
-            const int c = cv * 8 + 2 * t;
-            float a = f.x * sm[c] + sm[C + c];
-            float d = f.y * sm[c + 1] + sm[C + c + 1];
+            float a = f.x * sc[2 * t] + sh[2 * t];
+            float d = f.y * sc[2 * t + 1] + sh[2 * t + 1];
             if (silu) { a = silu_f(a); d = silu_f(d); }
             o[t] = pack_bf16x2(a, d);
         }
-        *reinterpret_cast<uint4*>(y + ((long long)b * HW + p) * ldy + cv * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        __stcs(reinterpret_cast<uint4*>(yb + p * ldy), make_uint4(o[0], o[1], o[2], o[3]));
+    };
+    int p = p0 + pl;
+    for (; p + 3 * kp < p1; p += 4 * kp) {      // four independent 16-byte loads in flight per thread
+        const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(xb + (long long)p * ldx));
+        const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(xb + (long long)(p + kp) * ldx));
+        const uint4 u2 = __ldg(reinterpret_cast<const uint4*>(xb + (long long)(p + 2 * kp) * ldx));
+        const uint4 u3 = __ldg(reinterpret_cast<const uint4*>(xb + (long long)(p + 3 * kp) * ldx));
+        one(u0, p); one(u1, p + kp); one(u2, p + 2 * kp); one(u3, p + 3 * kp);
     }
+    for (; p < p1; p += kp) one(__ldg(reinterpret_cast<const uint4*>(xb + (long long)p * ldx)), p);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -193,35 +217,25 @@ __global__ void sft_apply_kernel(const __nv_bfloat16* __restrict__ h, long long 
                                  long long ldo, int HW, int C, int G, const double* __restrict__ sums, double count,
                                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                  const float* __restrict__ control_scale, int pixels_per_block) {
-    extern __shared__ float sm[];
-    const int b = blockIdx.y;
-    const int cpg = C / G;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const int g = c / cpg;
-        const double dm = sums[((long long)b * G + g) * 2] / count;
-        double dv = sums[((long long)b * G + g) * 2 + 1] / count - dm * dm;
-        if (dv < 0) dv = 0;
-        const float rstd = rsqrtf((float)dv + eps);
-        const float sc = rstd * gamma[c];
-        sm[c] = sc;
-        sm[C + c] = beta[c] - (float)dm * sc;
-    }
-    __syncthreads();
-    const float cs = *control_scale;
     const int cv_count = C >> 3;
+    const int kp = blockDim.x / cv_count;
+    const int cv = threadIdx.x % cv_count;
+    const int pl = threadIdx.x / cv_count;
+    const int b = blockIdx.y;
+    const int c0 = cv * 8;
+    float sc[8], sh[8];
+    gn_scale_shift(b, c0, C, G, sums, count, nullptr, nullptr, gamma, beta, eps, sc, sh);
+    const float cs = *control_scale;
     const int p0 = blockIdx.x * pixels_per_block;
     const int p1 = min(p0 + pixels_per_block, HW);
-    const long long total = (long long)(p1 - p0) * cv_count;
-    for (long long i = threadIdx.x; i < total; i += blockDim.x) {
-        const int p = p0 + (int)(i / cv_count);
-        const int cv = (int)(i % cv_count);
+    const bool from_skip = c0 >= C1;
+    auto one = [&](int p) {
         const long long row = (long long)b * HW + p;
-        const int c0 = cv * 8;
         const uint4 uh = __ldg(reinterpret_cast<const uint4*>(h + row * ldh + c0));
         const uint4 ug = __ldg(reinterpret_cast<const uint4*>(gb + row * ldgb + c0));
         const uint4 ub = __ldg(reinterpret_cast<const uint4*>(gb + row * ldgb + C + c0));
         uint4 ur = uh;
-        if (c0 >= C1) ur = __ldg(reinterpret_cast<const uint4*>(skip_raw + row * lds + (c0 - C1)));
+        if (from_skip) ur = __ldg(reinterpret_cast<const uint4*>(skip_raw + row * lds + (c0 - C1)));
         const uint32_t wh[4] = {uh.x, uh.y, uh.z, uh.w}, wg[4] = {ug.x, ug.y, ug.z, ug.w},
                        wb[4] = {ub.x, ub.y, ub.z, ub.w}, wr[4] = {ur.x, ur.y, ur.z, ur.w};
         uint32_t o[4];
@@ -229,15 +243,17 @@ __global__ void sft_apply_kernel(const __nv_bfloat16* __restrict__ h, long long 
         for (int t = 0; t < 4; ++t) {
             const float2 fh = unpack_bf16x2(wh[t]), fg = unpack_bf16x2(wg[t]), fb = unpack_bf16x2(wb[t]),
                          fr = unpack_bf16x2(wr[t]);
-            const int c = c0 + 2 * t;
             // normalised (fp32) * (gamma + 1) + beta, each intermediate rounded like the reference's bf16 tensors
-            const float n0 = fh.x * sm[c] + sm[C + c], n1 = fh.y * sm[c + 1] + sm[C + c + 1];
+            const float n0 = fh.x * sc[2 * t] + sh[2 * t], n1 = fh.y * sc[2 * t + 1] + sh[2 * t + 1];
             const float a = n0 * (bf16_round(fg.x + 1.f)) + fb.x;
             const float d = n1 * (bf16_round(fg.y + 1.f)) + fb.y;
             o[t] = pack_bf16x2(a * cs + fr.x * (1.f - cs), d * cs + fr.y * (1.f - cs));
         }
-        *reinterpret_cast<uint4*>(out + row * ldo + c0) = make_uint4(o[0], o[1], o[2], o[3]);
-    }
+        __stcs(reinterpret_cast<uint4*>(out + row * ldo + c0), make_uint4(o[0], o[1], o[2], o[3]));
+    };
+    int p = p0 + pl;
+    for (; p + kp < p1; p += 2 * kp) { one(p); one(p + kp); }
+    for (; p < p1; p += kp) one(p);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -446,11 +462,14 @@ extern "C" int supir_groupnorm_apply(const void* x, long long ldx, void* y, long
     SUPIR_REQUIRE(x && y && (sums || (mean && var)), "supir_groupnorm_apply: null pointer");
     SUPIR_REQUIRE(C % 8 == 0 && C % groups == 0 && ldx % 8 == 0 && ldy % 8 == 0 && C <= 8192,
                   "supir_groupnorm_apply: bad C=%d", C);
-    int threads = 256;
-    int ppb = 16384 / C;  // ~32 KB of bf16 per block
-    if (ppb < 4) ppb = 4;
+    const int cvc = C >> 3;
+    int kp = 512 / cvc;
+    if (kp < 1) kp = 1;
+    const int threads = kp * cvc;
+    int ppb = kp * 32;              // 32 pixels per thread amortise the per-thread scale / shift set-up
+    if (ppb > HW) ppb = (HW + kp - 1) / kp * kp;
     const int bx = (HW + ppb - 1) / ppb;
-    gn_apply_kernel<<<dim3(bx, B), threads, 2 * C * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
+    gn_apply_kernel<<<dim3(bx, B), threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<__nv_bfloat16*>(y), ldy, HW, C, groups, mean,
         var, sums, (double)HW * (C / groups), gamma, beta, eps, silu, ppb);
     count_launch();
@@ -464,10 +483,14 @@ extern "C" int supir_zerosft_apply(const void* h, long long ldh, const void* ski
                                    float eps, const float* control_scale, void* stream) {
     SUPIR_REQUIRE(h && gamma_beta && out && sums && gn_weight && gn_bias && control_scale, "supir_zerosft_apply: null pointer");
     SUPIR_REQUIRE(C % 8 == 0 && C1 % 8 == 0 && C % groups == 0 && (C1 == C || skip_raw), "supir_zerosft_apply: bad channels");
-    int ppb = 8192 / C;
-    if (ppb < 4) ppb = 4;
+    SUPIR_REQUIRE(C <= 8192, "supir_zerosft_apply: C=%d too large", C);
+    const int cvc = C >> 3;
+    int kp = 512 / cvc;
+    if (kp < 1) kp = 1;
+    int ppb = kp * 16;
+    if (ppb > HW) ppb = (HW + kp - 1) / kp * kp;
     const int bx = (HW + ppb - 1) / ppb;
-    sft_apply_kernel<<<dim3(bx, B), 256, 2 * C * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
+    sft_apply_kernel<<<dim3(bx, B), kp * cvc, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const __nv_bfloat16*>(h), ldh, reinterpret_cast<const __nv_bfloat16*>(skip_raw), lds, C1,
         reinterpret_cast<const __nv_bfloat16*>(gamma_beta), ldgb, reinterpret_cast<__nv_bfloat16*>(out), ldo, HW, C,
         groups, sums, (double)HW * (C / groups), gn_weight, gn_bias, eps, control_scale, ppb);
