@@ -31,8 +31,6 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* d
 static constexpr int ATT_BM = 128;   // queries per tile (two tiles per CTA)
 static constexpr int ATT_BN = 128;   // keys per block
 static constexpr int ATT_D = 64;
-static constexpr int ATT_STAGES = 4;
-static constexpr int ATT_THREADS = 384;   // warpgroup 0: TMA + MMA (+2 idle warps), warpgroups 1/2: softmax of tile A/B
 static constexpr float ATT_RESCALE_THRESHOLD = 8.0f;   // log2 units
 
 struct AttnParams {
@@ -45,20 +43,29 @@ struct AttnParams {
     uint32_t idesc_pv;     // 128x64,  A K-major, B MN-major
 };
 
+// TILES = 128-query tiles per CTA, STAGES = K/V ring depth. <2, 4>: one CTA per SM, two tiles ping-pong (self-attention).
+// <1, 1>: single-block keys (77-token cross-attention): a light CTA (48 KB of shared memory, 256 TMEM columns, 256
+// threads) so that two or three share an SM and one CTA's load / store latency hides behind another's math.
+template <int TILES, int STAGES>
 struct AttnSmem {
     static constexpr int Q_BYTES = ATT_BM * ATT_D * 2;          // 16 KB per tile
     static constexpr int K_BYTES = ATT_BN * ATT_D * 2;          // 16 KB
     static constexpr int V_BYTES = ATT_BN * ATT_D * 2;          // 16 KB
     static constexpr int OFF_Q = 0;
-    static constexpr int OFF_K = OFF_Q + 2 * Q_BYTES;
-    static constexpr int OFF_V = OFF_K + ATT_STAGES * K_BYTES;
-    static constexpr int OFF_BAR = OFF_V + ATT_STAGES * V_BYTES;
+    static constexpr int OFF_K = OFF_Q + TILES * Q_BYTES;
+    static constexpr int OFF_V = OFF_K + STAGES * K_BYTES;
+    static constexpr int OFF_BAR = OFF_V + STAGES * V_BYTES;
     static constexpr int TOTAL = OFF_BAR + 256 + 1024;
 };
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+template <int TILES, int STAGES>
+__global__ void __launch_bounds__(128 + 128 * TILES, TILES == 1 ? 2 : 1)
 attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+    using AttnSmem = supir::AttnSmem<TILES, STAGES>;
+    constexpr int ATT_STAGES = STAGES;
+    constexpr uint32_t TMEM_COLS = TILES == 2 ? 512 : 256;
+    constexpr uint32_t COL_O = TILES * ATT_BN, COL_P = TILES * ATT_BN + TILES * ATT_D;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem + AttnSmem::OFF_Q;
@@ -76,8 +83,8 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qblk = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
     const int nblk = (p.Lk + ATT_BN - 1) / ATT_BN;
-    const int q0 = qblk * 2 * ATT_BM;                           // first query row of this CTA (within the batch element)
-    const bool tileB_valid = (q0 + ATT_BM) < p.Lq;               // CTA-uniform
+    const int q0 = qblk * TILES * ATT_BM;                           // first query row of this CTA (within the batch element)
+    const bool tileB_valid = TILES == 2 && (q0 + ATT_BM) < p.Lq;  // CTA-uniform
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ);
@@ -93,7 +100,7 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_ptr, 512);
+        tmem_alloc(tmem_ptr, TMEM_COLS);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -103,6 +110,7 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     // TMEM columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512) (bf16 pairs)
 
     if (warp < 4) {
+      // register budgets: <2,*> 384 threads x 168 -> 56 / 224;  <1,*> 256 threads x 128 (two CTAs per SM) -> 56 / 200
       asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
       if (warp == 0) {
         if (lane == 0) {
@@ -155,7 +163,7 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     for (int k = 0; k < ATT_BN / 16; ++k) {
                         // A = P in TMEM: 16 k-elements = 8 columns per step; B = V: MN-major (d contiguous), 16 kv rows of 128 B
                         const uint32_t va = vbase + k * 16 * 128;
-                        umma_bf16_ts(tmem_base + 256 + x * ATT_D, tmem_base + 384 + x * 64 + k * 8,
+                        umma_bf16_ts(tmem_base + COL_O + x * ATT_D, tmem_base + COL_P + x * 64 + k * 8,
                                      dtemplate | ((va >> 4) & 0x3FFF), p.idesc_pv, (j | k) != 0);
                     }
                     umma_commit(&pv_done[x]);
@@ -167,7 +175,8 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
       }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        if (TILES == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
         // ---------------- softmax / output warps ----------------
         const int x = (warp - 4) >> 2;                          // tile 0 (A) or 1 (B)
         if (x == 0 || tileB_valid) {
@@ -175,8 +184,8 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             const int row = quad * 32 + lane;                   // query row inside the tile
             const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
             const uint32_t tS = tmem_base + x * ATT_BN + lane_off;
-            const uint32_t tO = tmem_base + 256 + x * ATT_D + lane_off;
-            const uint32_t tP = tmem_base + 384 + x * 64 + lane_off;
+            const uint32_t tO = tmem_base + COL_O + x * ATT_D + lane_off;
+            const uint32_t tP = tmem_base + COL_P + x * 64 + lane_off;
             float m_ref = 0.f, l_run = 0.f;
             for (int j = 0; j < nblk; ++j) {
                 mbar_wait(&s_full[x], j & 1);
@@ -285,12 +294,28 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
 static long long g_att_desc_override = -1;
 static long long g_att_idesc_pv_override = -1;
+
+template <int TILES, int STAGES>
+static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnParams& p, int B,
+                            cudaStream_t st) {
+    using S = AttnSmem<TILES, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SUPIR_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<TILES, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+        attr_set = true;
+    }
+    dim3 grid((p.Lq + TILES * ATT_BM - 1) / (TILES * ATT_BM), p.H, B);
+    attention_d64_kernel<TILES, STAGES><<<grid, 128 + 128 * TILES, S::TOTAL, st>>>(tmQ, tmK, tmV, p);
+    count_launch();
+    SUPIR_CHECK_CUDA(cudaGetLastError());
+    return SUPIR_OK;
+}
 
 }  // namespace supir
 
@@ -309,11 +334,6 @@ extern "C" int supir_attention_bf16(const void* q, long long ldq, const void* k,
     SUPIR_REQUIRE(head_dim == 64, "supir_attention_bf16: head_dim %d unsupported (64 only)", head_dim);
     SUPIR_REQUIRE(B > 0 && H > 0 && Lq > 0 && Lk > 0, "supir_attention_bf16: bad shape");
     SUPIR_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "supir_attention_bf16: leading dims must be multiples of 8");
-    static bool attr_set = false;
-    if (!attr_set) {
-        SUPIR_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::TOTAL));
-        attr_set = true;
-    }
     CUtensorMap tmQ, tmK, tmV;
     const uint32_t box[2] = {ATT_D, ATT_BM};
     int rc;
@@ -339,9 +359,9 @@ extern "C" int supir_attention_bf16(const void* q, long long ldq, const void* k,
     p.desc_hi = (uint32_t)(dt >> 32);
     p.idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN, 0, 0);
     p.idesc_pv = g_att_idesc_pv_override >= 0 ? (uint32_t)g_att_idesc_pv_override : umma_idesc_bf16(ATT_BM, ATT_D, 0, 1);
-    dim3 grid((Lq + 2 * ATT_BM - 1) / (2 * ATT_BM), H, B);
-    attention_d64_kernel<<<grid, ATT_THREADS, AttnSmem::TOTAL, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
-    count_launch();
-    SUPIR_CHECK_CUDA(cudaGetLastError());
-    return SUPIR_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // one key block (77-token cross-attention): light one-tile CTAs, two per SM. One-tile CTAs measured no better than the
+    // two-tile kernel for multi-block self-attention (745 vs 762 TFLOP/s at 4096 tokens), so that keeps the ping-pong.
+    if (Lk <= ATT_BN) return launch_attention<1, 1>(tmQ, tmK, tmV, p, B, st);
+    return launch_attention<2, 4>(tmQ, tmK, tmV, p, B, st);
 }

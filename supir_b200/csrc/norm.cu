@@ -309,7 +309,7 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long 
             for (int t = 0; t < 4; ++t)
                 o[t] = pack_bf16x2((v[i][2 * t] - mean) * rstd * gg[2 * t] + bb[2 * t],
                                    (v[i][2 * t + 1] - mean) * rstd * gg[2 * t + 1] + bb[2 * t + 1]);
-            *reinterpret_cast<uint4*>(y + row * ldy + vi * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+            __stcs(reinterpret_cast<uint4*>(y + row * ldy + vi * 8), make_uint4(o[0], o[1], o[2], o[3]));
         }
     }
 }

@@ -28,6 +28,48 @@ def record_shapes(path):
     atexit.register(lambda: json.dump(log, open(path, "w")))
 
 
+def breakdown(w, B, hw):
+    """Per-op device time of one eager pass over the captured plan: every supir_b200.ops launch between a CUDA-event pair."""
+    import inspect, collections
+    from supir_b200 import ops
+    names = [n for n, f in vars(ops).items() if inspect.isfunction(f) and f.__module__ == ops.__name__ and not n.startswith("_")
+             and n not in ("groupnorm_ws_size",)]
+    rec, orig = [], {}
+    for n in names:
+        f = orig[n] = getattr(ops, n)
+
+        def wrap(*a, _f=f, _n=n, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = _f(*a, **kw)
+            e1.record()
+            key = _n
+            if _n == "attention":      # q [B*Lq, H*64], k [B*Lk, H*64]: split self- from cross-attention and by level
+                key = f"attention q{tuple(a[0].shape)} k{tuple(a[1].shape)}"
+            rec.append((key, e0, e1))
+            return r
+        setattr(ops, n, wrap)
+    plan = w._plans[max(w._plans, key=lambda k: k[0])]
+    try:
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        plan._run()
+        t1.record()
+        torch.cuda.synchronize()
+    finally:
+        for n, f in orig.items():
+            setattr(ops, n, f)
+    agg = collections.Counter()
+    cnt = collections.Counter()
+    for n, e0, e1 in rec:
+        agg[n] += e0.elapsed_time(e1)
+        cnt[n] += 1
+    tot = sum(agg.values())
+    print(f"== eager pass B={B} latent={hw}: wall {t0.elapsed_time(t1):.1f} ms, sum of op times {tot:.1f} ms, {len(rec)} calls")
+    for n, t in agg.most_common():
+        print(f"   {n:24s} {t:9.2f} ms {100*t/tot:5.1f}%  n={cnt[n]}")
+
+
 def main():
     if os.environ.get("BENCH_SHAPE_LOG"):
         record_shapes(os.environ["BENCH_SHAPE_LOG"])
@@ -64,6 +106,8 @@ def main():
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / iters
             fl = FLOP.get(hw, 0) * B / 2
+            if os.environ.get("BENCH_BREAKDOWN") == "1":
+                breakdown(w, B, hw)
             print(json.dumps({"latent": hw, "B": B, "ms": round(ms, 3), "tflops": round(fl / ms / 1e9, 1), "launches": launches,
                               "finite": bool(torch.isfinite(out).all()), "mem_gib": round(torch.cuda.max_memory_allocated() / 2**30, 1)}), flush=True)
 

@@ -573,6 +573,12 @@ int main(int argc, char** argv) {
         perf_attention(2, 10, 4096, 77);
         perf_attention(2, 20, 1024, 77);
     }
+    if (what == "attnperf2") {   // the shapes of the 49-window step (batch 98)
+        perf_attention(98, 10, 4096, 4096);
+        perf_attention(98, 20, 1024, 1024);
+        perf_attention(98, 10, 4096, 77);
+        perf_attention(98, 20, 1024, 77);
+    }
     if (what == "sanitize") {   // small cases for compute-sanitizer (memcheck / racecheck / synccheck)
         for (int bn : {0, 64, 160}) {
             supir_set_gemm_tile_n(bn);
