@@ -264,52 +264,70 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long 
                                  long long ldy, long long rows, int C, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, float eps) {
     const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int nv = C >> 3;
-    float v[MAXV][8];
-    float s = 0.f;
+    // a warp walks rows with stride nwarps; the next row's loads are issued before this row's reductions, so the two warp
+    // reductions between load and store no longer leave the memory pipe idle
+    uint4 nxt[MAXV];
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
         const int vi = lane + i * 32;
-        if (vi < nv) {
-            const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + row * ldx + vi * 8));
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        if (vi < nv) nxt[i] = __ldg(reinterpret_cast<const uint4*>(x + row * ldx + vi * 8));
+    }
+    for (; row < rows; row += nwarps) {
+        float v[MAXV][8];
+        float s = 0.f;
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const float2 f = unpack_bf16x2(w[t]);
-                v[i][2 * t] = f.x; v[i][2 * t + 1] = f.y;
-                s += f.x + f.y;
+        for (int i = 0; i < MAXV; ++i) {
+            const int vi = lane + i * 32;
+            if (vi < nv) {
+                const uint32_t w[4] = {nxt[i].x, nxt[i].y, nxt[i].z, nxt[i].w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const float2 f = unpack_bf16x2(w[t]);
+                    v[i][2 * t] = f.x; v[i][2 * t + 1] = f.y;
+                    s += f.x + f.y;
+                }
             }
         }
-    }
-    const float mean = warp_sum(s) / C;
-    float q = 0.f;
+        const long long nrow = row + nwarps;
+        if (nrow < rows) {
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-        const int vi = lane + i * 32;
-        if (vi < nv) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; q += d * d; }
+            for (int i = 0; i < MAXV; ++i) {
+                const int vi = lane + i * 32;
+                if (vi < nv) nxt[i] = __ldg(reinterpret_cast<const uint4*>(x + nrow * ldx + vi * 8));
+            }
         }
-    }
-    const float rstd = rsqrtf(warp_sum(q) / C + eps);
+        const float mean = warp_sum(s) / C;
+        float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-        const int vi = lane + i * 32;
-        if (vi < nv) {
-            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
-            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
-            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            uint32_t o[4];
+        for (int i = 0; i < MAXV; ++i) {
+            const int vi = lane + i * 32;
+            if (vi < nv) {
 #pragma unroll
-            for (int t = 0; t < 4; ++t)
-                o[t] = pack_bf16x2((v[i][2 * t] - mean) * rstd * gg[2 * t] + bb[2 * t],
-                                   (v[i][2 * t + 1] - mean) * rstd * gg[2 * t + 1] + bb[2 * t + 1]);
-            __stcs(reinterpret_cast<uint4*>(y + row * ldy + vi * 8), make_uint4(o[0], o[1], o[2], o[3]));
+                for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; q += d * d; }
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(q) / C + eps);
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int vi = lane + i * 32;
+            if (vi < nv) {
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+                const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
+                const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                uint32_t o[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    o[t] = pack_bf16x2((v[i][2 * t] - mean) * rstd * gg[2 * t] + bb[2 * t],
+                                       (v[i][2 * t + 1] - mean) * rstd * gg[2 * t + 1] + bb[2 * t + 1]);
+                __stcs(reinterpret_cast<uint4*>(y + row * ldy + vi * 8), make_uint4(o[0], o[1], o[2], o[3]));
+            }
         }
     }
 }
@@ -504,7 +522,9 @@ extern "C" int supir_layernorm_bf16(const void* x, long long ldx, void* y, long 
     SUPIR_REQUIRE(x && y && gamma && beta, "supir_layernorm_bf16: null pointer");
     SUPIR_REQUIRE(C % 8 == 0 && C <= 2048 && ldx % 8 == 0 && ldy % 8 == 0, "supir_layernorm_bf16: unsupported C=%d", C);
     const int warps = 8;
-    const long long blocks = (rows + warps - 1) / warps;
+    long long blocks = (rows + warps - 1) / warps;
+    const long long cap = (long long)device_sm_count() * 16;       // a few resident waves; warps then loop over rows
+    if (blocks > cap) blocks = cap;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
     __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
