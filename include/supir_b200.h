@@ -74,6 +74,12 @@ int supir_debug_set_umma_descriptors(long long smem_desc_template, long long ide
 int supir_conv3x3_small_cin(const float* x, long long sb, long long sc, long long sy, const float* w, const float* bias,
                             const void* residual, long long ldr, void* out, long long ldo, int B, int H, int W, int Cin,
                             int Cout, void* stream);
+/* im2col for the same layers as a tensor-core GEMM operand: row p of `out` ([B*H*W, ldo >= KP] bf16) receives the 3x3
+ * neighbourhood of pixel p, k = ci * 9 + tap (the flattening of a [Cout][Cin][3][3] weight), zero padded to KP columns and
+ * at the image border. supir_gemm_bf16 against the [Cout, KP] weight then replaces supir_conv3x3_small_cin for large images. */
+int supir_im2col_3x3_small_cin(const float* x, long long sb, long long sc, long long sy, void* out, long long ldo, int B,
+                               int H, int W, int Cin, int KP, void* stream);
+
 /* 3x3 pad-1 conv, Cout in {3,4,8}: x NHWC bf16 [B,H,W,ldx]; w fp32 [Cout, 3, 3, Cin]; only the crop window
  * [crop_y0, crop_y0+crop_h) x [crop_x0, crop_x0+crop_w) of the tile is computed and written to
  * out[b*ob + c*oc + (y-crop_y0)*oy + (x-crop_x0)] (fp32, values rounded to bf16 as under autocast).
@@ -145,6 +151,10 @@ int supir_axpy_bf16(const void* a, long long lda, const void* y, long long ldy, 
                     int cols, const float* scale, void* stream);
 int supir_nchw_f32_to_nhwc_bf16(const float* x, void* y, long long ldy, int B, int C, int HW, void* stream);
 int supir_nhwc_bf16_to_nchw_f32(const void* x, long long ldx, float* y, int B, int C, int HW, void* stream);
+/* crop window [crop_y0, +crop_h) x [crop_x0, +crop_w) of an NHWC bf16 tile [B, H, W, ldx >= C] -> fp32 NCHW view with element
+ * strides (ob, oc, oy, 1): the exit of a network whose last conv ran on the tensor cores with Cout padded to 8 */
+int supir_nhwc_bf16_crop_to_nchw_f32(const void* x, long long ldx, float* y, long long ob, long long oc, long long oy, int B,
+                                     int H, int W, int C, int crop_y0, int crop_x0, int crop_h, int crop_w, void* stream);
 int supir_f32_to_bf16(const float* x, void* y, long long n, void* stream);
 /* timestep_embedding (sgm/modules/diffusionmodules/util.py:206-230), dim even, max_period 1e4 */
 int supir_timestep_embedding(const float* t, float* out, int B, int dim, void* stream);

@@ -26,6 +26,7 @@ _SIGS = {
     "supir_debug_force_direct_epilogue": [c_int],
     "supir_debug_set_umma_descriptors": [c_ll, c_ll],
     "supir_conv3x3_small_cin": [c_void_p, c_ll, c_ll, c_ll, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "supir_im2col_3x3_small_cin": [c_void_p, c_ll, c_ll, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "supir_conv3x3_small_cout": [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_ll, c_ll, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "supir_conv1x1_small_nchw": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_ll, c_float, c_void_p],
     "supir_groupnorm_stats": [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p],
@@ -43,6 +44,7 @@ _SIGS = {
     "supir_axpy_bf16": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p, c_void_p],
     "supir_nchw_f32_to_nhwc_bf16": [c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_void_p],
     "supir_nhwc_bf16_to_nchw_f32": [c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_void_p],
+    "supir_nhwc_bf16_crop_to_nchw_f32": [c_void_p, c_ll, c_void_p, c_ll, c_ll, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "supir_f32_to_bf16": [c_void_p, c_void_p, c_ll, c_void_p],
     "supir_timestep_embedding": [c_void_p, c_void_p, c_int, c_int, c_void_p],
     "supir_linear_small_m": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p],

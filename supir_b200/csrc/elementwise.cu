@@ -104,6 +104,20 @@ __global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x
         y[i] = __bfloat162float(x[(b * HW + p) * ldx + c]);
     }
 }
+// crop window of an NHWC bf16 tile -> fp32 NCHW view with arbitrary strides (tiled-VAE paste; UNet output)
+__global__ void nhwc_bf16_crop_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, float* __restrict__ y,
+                                                  long long ob, long long oc, long long oy, int B, int H, int W, int C,
+                                                  int cy0, int cx0, int ch, int cw) {
+    const long long total = (long long)B * C * ch * cw;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int xo = (int)(i % cw);
+        long long r = i / cw;
+        const int yo = (int)(r % ch); r /= ch;
+        const int c = (int)(r % C);
+        const int b = (int)(r / C);
+        y[b * ob + c * oc + yo * oy + xo] = __bfloat162float(x[(((long long)b * H + yo + cy0) * W + xo + cx0) * ldx + c]);
+    }
+}
 __global__ void f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         y[i] = __float2bfloat16_rn(x[i]);
@@ -335,6 +349,17 @@ extern "C" int supir_nchw_f32_to_nhwc_bf16(const float* x, void* y, long long ld
 extern "C" int supir_nhwc_bf16_to_nchw_f32(const void* x, long long ldx, float* y, int B, int C, int HW, void* stream) {
     SUPIR_REQUIRE(x && y, "supir_nhwc_bf16_to_nchw_f32: null pointer");
     nhwc_bf16_to_nchw_f32_kernel<<<blocks_for((long long)B * C * HW, 256), 256, 0, ST(stream)>>>(CBF(x), ldx, y, B, C, HW);
+    DONE();
+}
+
+extern "C" int supir_nhwc_bf16_crop_to_nchw_f32(const void* x, long long ldx, float* y, long long ob, long long oc, long long oy,
+                                                int B, int H, int W, int C, int crop_y0, int crop_x0, int crop_h, int crop_w,
+                                                void* stream) {
+    SUPIR_REQUIRE(x && y, "supir_nhwc_bf16_crop_to_nchw_f32: null pointer");
+    SUPIR_REQUIRE(crop_y0 >= 0 && crop_x0 >= 0 && crop_h > 0 && crop_w > 0 && crop_y0 + crop_h <= H && crop_x0 + crop_w <= W,
+                  "supir_nhwc_bf16_crop_to_nchw_f32: crop window outside the tile");
+    nhwc_bf16_crop_to_nchw_f32_kernel<<<blocks_for((long long)B * C * crop_h * crop_w, 256), 256, 0, ST(stream)>>>(
+        CBF(x), ldx, y, ob, oc, oy, B, H, W, C, crop_y0, crop_x0, crop_h, crop_w);
     DONE();
 }
 

@@ -64,6 +64,38 @@ __global__ void conv3x3_small_cin_kernel(const float* __restrict__ x, long long 
     }
 }
 
+// -------- Cin <= 8 as a tensor-core GEMM: im2col of the fp32 NCHW input into bf16 rows [pixel][Cin*9 -> KP], zero padded ----
+// (k = ci * 9 + tap, the flattening of the weight [Cout][Cin][3][3]); the GEMM kernel then does bias / residual / store.
+__global__ void im2col_small_cin_kernel(const float* __restrict__ x, long long sb, long long sc, long long sy,
+                                        __nv_bfloat16* __restrict__ out, long long ldo, int B, int H, int W, int Cin, int KP) {
+    const int kv = KP >> 3;                       // 16-byte vectors per row
+    const long long total = (long long)B * H * W * kv;
+    const int taps = Cin * 9;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i % kv);
+        const long long pix = i / kv;
+        const int xx = (int)(pix % W);
+        const int r = (int)(pix / W);
+        const int yy = r % H, b = r / H;
+        float e[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = v * 8 + j;
+            float val = 0.f;
+            if (k < taps) {
+                const int ci = k / 9, t = k - ci * 9;
+                const int y2 = yy + t / 3 - 1, x2 = xx + t % 3 - 1;
+                if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) val = __ldg(x + b * sb + ci * sc + y2 * sy + x2);
+            }
+            e[j] = val;
+        }
+        uint4 o;
+        o.x = pack_bf16x2(e[0], e[1]); o.y = pack_bf16x2(e[2], e[3]);
+        o.z = pack_bf16x2(e[4], e[5]); o.w = pack_bf16x2(e[6], e[7]);
+        *reinterpret_cast<uint4*>(out + pix * ldo + v * 8) = o;
+    }
+}
+
 // -------- Cout <= 8 : one warp per output pixel; lanes split the (tap, channel-vector) products --------
 template <int COUT>
 __global__ void conv3x3_small_cout_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float* __restrict__ w,
@@ -158,6 +190,22 @@ extern "C" int supir_conv3x3_small_cin(const float* x, long long sb, long long s
     conv3x3_small_cin_kernel<<<(unsigned)blocks, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
         x, sb, sc, sy, w, bias, reinterpret_cast<const __nv_bfloat16*>(residual), ldr, reinterpret_cast<__nv_bfloat16*>(out),
         ldo, B, H, W, Cin, Cout);
+    count_launch();
+    SUPIR_CHECK_CUDA(cudaGetLastError());
+    return SUPIR_OK;
+}
+
+extern "C" int supir_im2col_3x3_small_cin(const float* x, long long sb, long long sc, long long sy, void* out, long long ldo,
+                                          int B, int H, int W, int Cin, int KP, void* stream) {
+    SUPIR_REQUIRE(x && out, "supir_im2col_3x3_small_cin: null pointer");
+    SUPIR_REQUIRE(Cin >= 1 && Cin <= 8 && KP % 8 == 0 && KP >= Cin * 9 && ldo >= KP && ldo % 8 == 0,
+                  "supir_im2col_3x3_small_cin: Cin=%d KP=%d unsupported", Cin, KP);
+    const long long total = (long long)B * H * W * (KP >> 3);
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)device_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    im2col_small_cin_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        x, sb, sc, sy, reinterpret_cast<__nv_bfloat16*>(out), ldo, B, H, W, Cin, KP);
     count_launch();
     SUPIR_CHECK_CUDA(cudaGetLastError());
     return SUPIR_OK;

@@ -109,11 +109,13 @@ class ConvIn(nn.Conv2d):
 
     def pack(self):
         self._w, self._b = self.weight.detach().to(BF16).to(torch.float32).contiguous(), _bias_bf16_values(self.bias)
+        self._wp = ops.pack_small_cin_weight(self.weight)
 
     def run_nchw(self, ctx, x_nchw, residual=None):
         B, _, H, W = x_nchw.shape
         out = ctx.new(B * H * W, self.out_channels)
-        ops.conv3x3_small_cin(x_nchw, self._w, self._b, out, residual=None if residual is None else residual.t)
+        ops.conv3x3_small_cin(x_nchw, self._w, self._b, out, residual=None if residual is None else residual.t,
+                              w_packed=self._wp, pool=ctx.pool)
         return Act(out, B, H, W)
 
 
@@ -619,6 +621,7 @@ class LightGLVUNet(_UNetBase):
         w = self.out[2].weight.detach()
         self._wout = w.to(BF16).to(torch.float32).permute(0, 2, 3, 1).contiguous()     # [Cout, 3, 3, Cin]
         self._bout = _bias_bf16_values(self.out[2].bias)
+        self._out_packed = ops.pack_small_cout_weight(w, self.out[2].bias)
         return self
 
     def run(self, ctx, x, t_f32, context_bf16, Lctx, y_f32, control, out_nchw):
@@ -662,7 +665,7 @@ class LightGLVUNet(_UNetBase):
             cidx -= 1
         n = group_norm(ctx, h, self.out[0], silu=True)
         ctx.free(h)
-        ops.conv3x3_small_cout(n.t, n.B, n.H, n.W, self._wout, self._bout, out_nchw)
+        ops.conv3x3_small_cout(n.t, n.B, n.H, n.W, self._wout, self._bout, out_nchw, packed=self._out_packed, pool=ctx.pool)
         ctx.free(n)
         self._release_ctx(ctx)
         return out_nchw

@@ -175,23 +175,60 @@ def softmax_rows(S, P, cols, scale):
 # ------------------------------------------------------------------------------------------------------------------
 # small convs, data movement, embeddings
 # ------------------------------------------------------------------------------------------------------------------
-def conv3x3_small_cin(x_nchw, w, bias, out, residual=None):
-    """x_nchw: fp32 [B, Cin, H, W] view with unit stride along W; out NHWC bf16 [B*H*W, Cout]."""
+def pack_small_cin_weight(w):
+    """[Cout, Cin, 3, 3] -> bf16 [Cout, KP] (k = ci*9 + tap, zero padded to a multiple of 64): GEMM operand of the im2col path."""
+    cout, taps = w.shape[0], w.shape[1] * 9
+    kp = (taps + 63) // 64 * 64
+    wp = torch.zeros(cout, kp, dtype=BF16, device=w.device)
+    wp[:, :taps] = w.detach().reshape(cout, taps).to(BF16)
+    return wp
+
+
+def conv3x3_small_cin(x_nchw, w, bias, out, residual=None, w_packed=None, pool=None):
+    """x_nchw: fp32 [B, Cin, H, W] view with unit stride along W; out NHWC bf16 [B*H*W, Cout].
+    With `w_packed` (pack_small_cin_weight) and a scratch `pool`, large images go through im2col + the tensor-core GEMM."""
     _need_cuda(x_nchw, w, out)
     B, Cin, H, W = x_nchw.shape
     assert x_nchw.dtype == torch.float32 and x_nchw.stride(3) == 1 and w.dtype == torch.float32 and w.is_contiguous()
+    if w_packed is not None and pool is not None and B * H * W >= 16384 and out.shape[1] >= 64:
+        kp = w_packed.shape[1]
+        cols = pool.get((B * H * W, kp))
+        call("supir_im2col_3x3_small_cin", _ptr(x_nchw), x_nchw.stride(0), x_nchw.stride(1), x_nchw.stride(2), _ptr(cols),
+             cols.stride(0), B, H, W, Cin, kp, _stream())
+        gemm(cols, w_packed, out, bias=bias, residual=residual)
+        pool.put(cols)
+        return out
     call("supir_conv3x3_small_cin", _ptr(x_nchw), x_nchw.stride(0), x_nchw.stride(1), x_nchw.stride(2), _ptr(w), _ptr(bias),
          _ptr(residual), 0 if residual is None else residual.stride(0), _ptr(out), out.stride(0), B, H, W, Cin, out.shape[1],
          _stream())
     return out
 
 
-def conv3x3_small_cout(x, B, H, W, w, bias, out_nchw, crop=None):
-    """x NHWC bf16 [B*H*W, Cin]; out_nchw fp32 [B, Cout, h, w] view (unit stride along w) receiving the crop window."""
+def pack_small_cout_weight(w, bias):
+    """[Cout <= 8, Cin, 3, 3] -> (bf16 [8, 9*Cin] in conv3x3's (kh, kw, cin) order, fp32 bias[8]), zero rows beyond Cout."""
+    cout, cin = w.shape[0], w.shape[1]
+    wp = torch.zeros(8, 9 * cin, dtype=BF16, device=w.device)
+    wp[:cout] = w.detach().permute(0, 2, 3, 1).reshape(cout, -1).to(BF16)
+    b8 = torch.zeros(8, dtype=torch.float32, device=w.device)
+    if bias is not None:
+        b8[:cout] = bias.detach().to(BF16).to(torch.float32)
+    return wp, b8
+
+
+def conv3x3_small_cout(x, B, H, W, w, bias, out_nchw, crop=None, packed=None, pool=None):
+    """x NHWC bf16 [B*H*W, Cin]; out_nchw fp32 [B, Cout, h, w] view (unit stride along w) receiving the crop window.
+    With `packed` (pack_small_cout_weight) and a scratch `pool`, large images run on the tensor cores (Cout padded to 8)."""
     _need_cuda(x, w, out_nchw)
     _mat(x)
     y0, x0, ch, cw = crop if crop is not None else (0, 0, H, W)
     assert out_nchw.dtype == torch.float32 and out_nchw.stride(3) == 1 and tuple(out_nchw.shape[2:]) == (ch, cw)
+    if packed is not None and pool is not None and B * H * W >= 16384 and x.shape[1] % 64 == 0:
+        tmp = pool.get((B * H * W, 8))
+        conv3x3(x, B, H, W, packed[0], tmp, bias=packed[1])
+        call("supir_nhwc_bf16_crop_to_nchw_f32", _ptr(tmp), tmp.stride(0), _ptr(out_nchw), out_nchw.stride(0), out_nchw.stride(1),
+             out_nchw.stride(2), B, H, W, out_nchw.shape[1], y0, x0, ch, cw, _stream())
+        pool.put(tmp)
+        return out_nchw
     call("supir_conv3x3_small_cout", _ptr(x), x.stride(0), _ptr(w), _ptr(bias), _ptr(out_nchw), out_nchw.stride(0),
          out_nchw.stride(1), out_nchw.stride(2), B, H, W, x.shape[1], out_nchw.shape[1], y0, x0, ch, cw, _stream())
     return out_nchw

@@ -110,6 +110,7 @@ class _VAENet(nn.Module):
 
         ci = self.conv_in
         self._conv_in = (ci.weight.detach().to(BF16).to(torch.float32).contiguous(), _bias_bf16_values(ci.bias), ci.out_channels)
+        self._conv_in_packed = ops.pack_small_cin_weight(ci.weight)
         mid = lambda: (resblock(self.mid.block_1), attn(self.mid.attn_1), resblock(self.mid.block_2))  # noqa: E731
         if self.is_decoder:
             mid()
@@ -131,6 +132,7 @@ class _VAENet(nn.Module):
         co = self.conv_out
         self._conv_out = (co.weight.detach().to(BF16).to(torch.float32).permute(0, 2, 3, 1).contiguous(),
                           _bias_bf16_values(co.bias), co.out_channels)
+        self._conv_out_packed = ops.pack_small_cout_weight(co.weight, co.bias)
         self._packed = True
         return self
 
@@ -242,13 +244,13 @@ class _VAENet(nn.Module):
         B, _, H, W = x_view.shape
         w, b, cout = self._conv_in
         out = pool.get((B * H * W, cout))
-        ops.conv3x3_small_cin(x_view, w, b, out)
+        ops.conv3x3_small_cin(x_view, w, b, out, w_packed=self._conv_in_packed, pool=pool)
         return {"h": Act(out, B, H, W), "res": [], "one": self._one}
 
     def _finish_tile(self, pool, tile, out_view, crop=None):
         a: Act = tile["h"]
         w, b, cout = self._conv_out
-        ops.conv3x3_small_cout(a.t, a.B, a.H, a.W, w, b, out_view, crop=crop)
+        ops.conv3x3_small_cout(a.t, a.B, a.H, a.W, w, b, out_view, crop=crop, packed=self._conv_out_packed, pool=pool)
         pool.put(a.t)
 
     def _fused_steps(self):
