@@ -121,6 +121,37 @@ def test_small_convs_and_conv1x1():
     close(y.cpu(), ref, 2e-2)
 
 
+def test_entry_exit_convs_on_tensor_cores_match_cuda_core_kernels():
+    """Large images route the Cin<=8 / Cout<=8 convs through im2col + tcgen05 GEMM / the padded implicit-GEMM conv
+    (ops.conv3x3_small_cin / _small_cout with packed weights): same values as the CUDA-core kernels and as torch."""
+    ops = _ops()
+    pool = ops.Pool()
+    B, H, W = 1, 128, 136                           # >= 16384 pixels switches the path on
+    big = rnd((B, 4, H + 9, W + 11), 31).cuda()
+    tile = big[:, :, 4:4 + H, 6:6 + W]              # strided NCHW view, like a VAE tile
+    w = (rnd((320, 4, 3, 3), 32) * 0.2).to(BF).float()
+    b = (rnd((320,), 33) * 0.1).to(BF).float()
+    res = rnd((B * H * W, 320), 34).to(BF).cuda()
+    o_cc = torch.empty(B * H * W, 320, dtype=BF, device="cuda")
+    o_tc = torch.empty_like(o_cc)
+    ops.conv3x3_small_cin(tile, w.cuda(), b.cuda(), o_cc, residual=res)
+    ops.conv3x3_small_cin(tile, w.cuda(), b.cuda(), o_tc, residual=res, w_packed=ops.pack_small_cin_weight(w.cuda()), pool=pool)
+    ref = F.conv2d(tile.cpu().to(BF).float(), w, b, padding=1).to(BF).float() + from_nhwc(res, B, H, W).float()
+    close(from_nhwc(o_tc, B, H, W), ref, 3e-2)
+    close(o_tc.float().cpu(), o_cc.float().cpu(), 2e-2)
+    xin = rnd((B, 128, H, W), 35).to(BF)
+    for cout in (3, 4, 8):
+        wc = (rnd((cout, 128, 3, 3), 36 + cout) * 0.05).to(BF).float()
+        bc = (rnd((cout,), 37) * 0.1).to(BF).float()
+        ref = F.conv2d(xin.float(), wc, bc, padding=1).to(BF).float()
+        canvas = torch.zeros(B, cout, H + 10, W + 10, device="cuda")
+        dst = canvas[:, :, 5:5 + 100, 7:7 + 90]
+        ops.conv3x3_small_cout(nhwc(xin.float()), B, H, W, wc.permute(0, 2, 3, 1).contiguous().cuda(), bc.cuda(), dst,
+                               crop=(9, 11, 100, 90), packed=ops.pack_small_cout_weight(wc.cuda(), bc.cuda()), pool=pool)
+        close(dst.cpu(), ref[:, :, 9:109, 11:101], 3e-2)
+        assert float(canvas[:, :, :5].abs().max()) == 0.0 and float(canvas[:, :, :, :7].abs().max()) == 0.0
+
+
 def test_upsample_im2col_copy_axpy_layout():
     ops = _ops()
     B, C, H, W = 2, 64, 6, 10
