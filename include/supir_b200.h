@@ -159,7 +159,8 @@ int supir_f32_to_bf16(const float* x, void* y, long long n, void* stream);
 /* timestep_embedding (sgm/modules/diffusionmodules/util.py:206-230), dim even, max_period 1e4 */
 int supir_timestep_embedding(const float* t, float* out, int B, int dim, void* stream);
 /* y = [silu]( [silu](x) @ W^T + bias ) [+ add] for B <= 16 rows (time/label embedding MLPs, per-ResBlock emb_layers:
- * openaimodel.py:664-697, 287-293); x, y, add fp32; W bf16 [N, K] */
+ * openaimodel.py:664-697, 287-293); x, y, add fp32; W bf16 [N, K]. silu_out bit 0: SiLU before the add; bit 1: SiLU of the
+ * final sum (emb is only ever consumed through SiLU -> Linear, so its SiLU is computed once here instead of per consumer) */
 int supir_linear_small_m(const float* x, int ldx, const void* W, const float* bias, float* y, int ldy, int B, int N, int K,
                          int silu_in, int silu_out, const float* add, int ldadd, void* stream);
 /* sampler step, part 1 (sampling.py:550-556 + guiders.py:65-74 + denoiser.py:71): x_hat = x + eps*noise_mul (eps may be

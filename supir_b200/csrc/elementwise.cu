@@ -175,8 +175,9 @@ __global__ void linear_small_m_kernel(const float* __restrict__ x, int ldx, cons
             float v = warp_sum(acc[b]);
             if (lane == 0) {
                 v = bf16_round(v + (bias ? bias[n] : 0.f));
-                if (silu_out) v = bf16_round(silu_f(v));
+                if (silu_out & 1) v = bf16_round(silu_f(v));
                 if (add) v = bf16_round(v + add[b * ldadd + n]);
+                if (silu_out & 2) v = bf16_round(silu_f(v));     // SiLU of the sum: what every consumer of `emb` applies first
                 y[b * ldy + n] = v;
             }
         }

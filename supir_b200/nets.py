@@ -536,9 +536,10 @@ class _UNetBase(nn.Module):
         ops.linear_small_m(temb, self._te[0], self._te[1], h1, silu_out=True)
         ops.linear_small_m(h1, self._te[2], self._te[3], e_t)
         ops.linear_small_m(y_f32, self._le[0], self._le[1], h2, silu_out=True)
-        ops.linear_small_m(h2, self._le[2], self._le[3], emb, add=e_t)
+        # emb = time_embed(t) + label_emb(y) is only consumed through the ResBlocks' SiLU -> Linear: store SiLU(emb) once
+        ops.linear_small_m(h2, self._le[2], self._le[3], emb, add=e_t, silu_out=2)
         ctx.emb_all = p.get((B, self._emb_w.shape[0]), torch.float32)
-        ops.linear_small_m(emb, self._emb_w, self._emb_b, ctx.emb_all, silu_in=True)
+        ops.linear_small_m(emb, self._emb_w, self._emb_b, ctx.emb_all)
         p.put(temb, h1, e_t, h2, emb)
         ctx.ctx_kv = p.get((B * Lctx, self._ctx_kv_cols))
         ops.gemm(context_bf16, self._ctx_w, ctx.ctx_kv)
