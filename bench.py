@@ -71,7 +71,12 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.i0 = index, None, [], 0
+
+    def mark(self):
+        """Start of the timed region: samples read from here on are the ones reported. The process is started before the
+        warm-up steps because nvidia-smi needs up to a second to emit its first line on a multi-GPU box."""
+        self.i0 = len(self.lines)
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -91,8 +96,12 @@ class ClockSampler:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
+        window = "timed region"
+        lines = self.lines[self.i0:]
+        if not any(len(ln.split(",")) >= 7 for ln in lines):
+            lines, window = self.lines[-8:], "warm-up + timed steps (same load; no sample fell inside the short timed region)"
         sm, mx, reasons = [], None, set()
-        for ln in self.lines:
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -104,7 +113,8 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "window": window}
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -350,14 +360,15 @@ def run_supir(args):
     run = smp.begin(denoiser, noised, cond, ucond, x_center=z_stage1, control_scale=1.0)
 
     # ---- warm-up steps (graph capture happens in the first one) ----
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     for i in range(args.warmup):
         run.step(i)
     barrier()
     launches_per_step = None
     # ---- timed region: EXACTLY K EDM steps (device-resident) ----
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
+    clocks.mark()
     lc0 = _native.launch_count() + net.replayed_launches
     barrier()
     t0, t1 = ev(), ev()
