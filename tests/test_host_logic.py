@@ -138,3 +138,60 @@ def test_config_factory_resolves_reference_targets():
     smp = config.instantiate_from_config(dict(cfg["sampler_config"], params=dict(cfg["sampler_config"]["params"], device="cpu")))
     assert type(smp).__name__ == "TiledRestoreEDMSampler" and type(smp).__module__ == "supir_b200.sampling"
     assert smp.tile_size == 128 and smp.tile_stride == 64 and type(smp.guider).__name__ == "LinearCFG"
+
+
+def test_vae_step_fusion_plan():
+    """Host-side step list of the VAE nets (vae._VAENet.pack / _fused_steps): every SiLU is folded into the GroupNorm before
+    it and every skip-connection add into the conv / attention before it, so no standalone 'silu' or 'add_res' step runs."""
+    from supir_b200 import vae
+    cfg = dict(ch=32, out_ch=3, ch_mult=(1, 2), num_res_blocks=1, attn_resolutions=[], in_channels=3, resolution=32, z_channels=4)
+    for net in (vae.Encoder(double_z=True, **cfg), vae.Decoder(**cfg)):
+        net.pack()
+        raw = [s[0] for s in net._steps]
+        fused = net._fused_steps()
+        kinds = [s[0] for s, _ in fused]
+        assert "silu" not in kinds and "add_res" not in kinds
+        assert raw.count("silu") == sum(1 for s, f in fused if s[0] == "norm" and f)
+        assert raw.count("add_res") == sum(1 for s, f in fused if s[0] in ("conv", "attn") and f)
+        # every skip that is stored is consumed by exactly one fused add
+        assert raw.count("store_res") == raw.count("add_res")
+
+
+def test_entry_exit_conv_weight_packing():
+    """Tensor-core operands of the Cin<=8 / Cout<=8 convs: k = ci*9 + tap for the im2col GEMM, (kh, kw, cin) rows padded to
+    8 output channels for the implicit-GEMM conv; padding is zero so the extra columns / rows cannot leak into the result."""
+    from supir_b200 import ops
+    w = torch.randn(16, 4, 3, 3)
+    wp = ops.pack_small_cin_weight(w)
+    assert wp.shape == (16, 64) and wp.dtype == torch.bfloat16
+    assert torch.equal(wp[:, :36].float(), w.reshape(16, 36).to(torch.bfloat16).float()) and float(wp[:, 36:].abs().max()) == 0.0
+    assert ops.pack_small_cin_weight(torch.randn(8, 8, 3, 3)).shape == (8, 128)          # 72 taps -> two 64-column k-blocks
+    wc, bc = torch.randn(3, 16, 3, 3), torch.randn(3)
+    p, b8 = ops.pack_small_cout_weight(wc, bc)
+    assert p.shape == (8, 144) and b8.shape == (8,)
+    assert torch.equal(p[:3].float(), wc.permute(0, 2, 3, 1).reshape(3, -1).to(torch.bfloat16).float())
+    assert float(p[3:].abs().max()) == 0.0 and float(b8[3:].abs().max()) == 0.0
+    assert torch.equal(b8[:3], bc.to(torch.bfloat16).float())
+
+
+def test_bench_clock_sampler_windows():
+    """bench.ClockSampler reports the samples of the timed region, or, when the region was shorter than nvidia-smi's period,
+    the last samples of the warm-up + timed load, and says which."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class _P:
+        def terminate(self):
+            pass
+    c = bench.ClockSampler(0)
+    c.proc = _P()
+    c.lines = ["1500, 1965, 900.1, Not Active, Not Active, Not Active, Active"] * 3
+    c.mark()
+    r = c.stop()
+    assert r["sm_mhz"] == 1500.0 and r["reasons"] == ["sw_power_cap"] and r["window"].startswith("warm-up")
+    c.lines.append("1600, 1965, 910.0, Not Active, Not Active, Not Active, Not Active")
+    r = c.stop()
+    assert r["sm_mhz"] == 1600.0 and r["samples"] == 1 and r["window"] == "timed region" and r["reasons"] == []
+    assert bench.ClockSampler(0).stop()["sm_mhz"] is None
