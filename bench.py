@@ -277,7 +277,6 @@ def profile_dominant_kernel(net, device):
     plan._run()
     torch.cuda.synchronize()
     ops.gemm, ops.conv3x3 = gemm, conv
-    from supir_b200 import nets as _n
     try:
         plan._run()
         torch.cuda.synchronize()

@@ -3,8 +3,6 @@
 `wavelet_reconstruction(content, style)` keeps the high-frequency part of `content` (5 a-trous levels) and the low-frequency
 part of `style`; `adaptive_instance_normalization(content, style)` matches per-channel mean / std. Inputs are fp32 NCHW
 CUDA tensors as `SUPIRModel.batchify_sample` hands them over (SUPIR_model.py:131-135)."""
-import ctypes
-
 import torch
 
 from . import _native

@@ -5,8 +5,6 @@ The sigma tables are tiny host-side constants (float64 numpy -> float32), comput
 nearest-sigma quantisation is bit-identical. `DiscreteDenoiserWithControl.__call__` keeps the reference signature; its
 elementwise arithmetic runs in the fused CUDA kernels of supir_b200/csrc/elementwise.cu.
 """
-from functools import partial
-
 import numpy as np
 import torch
 import torch.nn as nn

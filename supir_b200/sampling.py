@@ -12,8 +12,6 @@ step runs:
     reference's window order (bit-identical x_{t+1} on all ranks; sampling.py:629-659).
 RNG stays in PyTorch (torch.randn_like in the reference's order); kernels take the noise as an input.
 """
-import math
-
 import numpy as np
 import torch
 
