@@ -15,8 +15,13 @@
 //   warp 1 lane 0 : tcgen05.mma issuer (UMMA 128 x BN x 16, accumulators in TMEM, double-buffered across tiles).
 //   warps 2..9    : epilogue, two warps per TMEM lane quadrant taking alternate 32-column chunks (tcgen05.ld of the next
 //                   chunk is in flight while the current one is converted and stored); +bias, +per-batch vector (timestep embedding),
-//                   SiLU / GEGLU, bf16 round, +residual, 64-byte-contiguous global stores.
+//                   SiLU / GEGLU, bf16 round, +residual (a TMA-loaded tile), swizzled shared-memory staging and a TMA
+//                   store per chunk; a direct-store fallback serves fp32 outputs and unaligned shapes.
 // Pipelines: smem full/empty ring (TMA <-> MMA) and TMEM full/empty (MMA <-> epilogue).
+// CTAS = 2 (template parameter): the same kernel on a 2-CTA cluster, one 256 x BN tile per pair with
+// tcgen05.mma.cta_group::2 — CTA r owns rows [128 r, 128 r + 128), loads its own A tile and half of the W tile with the
+// bytes credited to CTA 0's mbarrier; CTA 0 issues the MMAs for both and multicasts the commits; the peer's epilogue warps
+// release the accumulator with a remote mbarrier arrive.
 #include "common.cuh"
 #include "supir_b200.h"
 
