@@ -135,6 +135,9 @@ int supir_softmax_rows(const float* S, long long lds, void* P, long long ldp, lo
 int supir_attention_bf16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                          void* out, long long ldo, int B, int H, int Lq, int Lk, int head_dim, float scale, void* stream);
 int supir_debug_set_attention_descriptors(long long smem_desc_template, long long idesc_pv);
+/* tuning knob: how many of every 4 element pairs of the softmax take 2^x from the FMA-pipe polynomial instead of MUFU.EX2
+ * (0..4; default 2 or the environment variable SUPIR_B200_ATTN_EMU; negative restores the default). */
+int supir_set_attention_exp_emulation(int pairs_of_4);
 
 /* ------------------------------------------------------------------------------------------------------------------ */
 /* K7/K8/K10/K12/K14 and data movement (elementwise.cu)                                                               */

@@ -4,31 +4,40 @@
 // (sgm/modules/attention.py:273-277, 357-359) for self-attention, 77-token cross-attention and ZeroCrossAttn
 // (SUPIR/modules/SUPIR_v0.py:146).
 //
-// One CTA = one (batch, head) and 256 queries = two 128-row tiles A and B; 384 threads (3 warpgroups; the softmax
-// warpgroups take the registers the control warpgroup gives up via setmaxnreg, so a whole S row lives in registers):
-//   warp 0 lane 0 : TMA producer (Q_A, Q_B once; K/V 128-row blocks through a 3-stage ring, shared by both tiles)
-//   warp 1 lane 0 : tcgen05.mma issuer. Per tile X and key block j:
-//                     S_X = Q_X K_j^T   (128x128x64, TMEM, overwritten every block)
-//                     O_X += P_X V_j    (128x64x128, ACCUMULATED in TMEM across blocks)
+// PERSISTENT kernel: one CTA per SM (two for the one-tile variant) walks work items (batch, head, query block) with stride
+// gridDim.x; barriers and TMEM are set up once. 128 + 128*TILES threads, warp-specialised:
+//   warp 0 lane 0 : TMA producer. Q of the NEXT item is fetched into the second Q buffer while the current item computes;
+//                   K/V 128-row blocks run through one ring that simply continues across items.
+//   warp 1 lane 0 : tcgen05.mma issuer. Per tile X (128 query rows) and key block j:
+//                     S_X = Q_X K_j^T   (128 x NKEY x 64, TMEM, overwritten every block)
+//                     O_X += P_X V_j    (128 x 64 x NKEY, ACCUMULATED in TMEM across the blocks of an item)
 //                   with P_X read straight from TENSOR MEMORY (A-in-TMEM form of tcgen05.mma: P never touches shared
 //                   memory, whose bandwidth the QK/PV operand reads already saturate) and V consumed in its natural
-//                   [kv, d] layout as an MN-major B operand.
-//   warps 4..7    : softmax group of tile A, warps 8..11: tile B — one query row per thread. The whole S row (128 fp32) is
-//                   read from TMEM once into registers; p = ex2((s - m) * scale) is packed to bf16 pairs and stored back to
-//                   TMEM (tcgen05.st, 64 columns per tile) as the A operand of the PV MMA.
-// Online softmax without touching O every block: the exponent reference m is only moved when the running row maximum
-// exceeds it by more than 8 (p <= 2^8 stays exact enough in bf16/fp32); only then the warp rescales its 32 rows of O in
-// TMEM (tcgen05.ld / tcgen05.st) and its row sum. Two independent tiles keep the tensor pipe and the MUFU pipe busy
-// while the other tile waits on a dependency; the ex2 throughput (16/clk/SM) is this kernel's roofline, not the MMA.
+//                   [kv, d] layout as an MN-major B operand. The first QK of the next item is issued while the softmax
+//                   warps still normalise and store the current item's O.
+//   warps 4..7    : softmax group of tile A, warps 8..11: tile B — one query row per thread. The whole S row is read from
+//                   TMEM once into registers; p = 2^((s - m) * scale) is packed to bf16 pairs and stored back to TMEM
+//                   (tcgen05.st) as the A operand of the PV MMA.
+// The softmax is the bound of this kernel, not the MMA: at head_dim 64 a key block costs 512 tensor-pipe cycles per tile but
+// 128 ex2 per row = 1024 MUFU cycles per warp (MUFU: 4 lanes/clk per SM sub-partition). So
+//   * the arithmetic around the exponential runs on PACKED fp32 pairs (fma/add.f32x2 -> FFMA2/FADD2: half the issue slots);
+//   * EMU of every 4 element pairs take their exponential on the FMA pipe instead of MUFU: Cody-Waite split
+//     x = n + f (add.rm with the 1.5*2^23 magic constant), degree-3 minimax polynomial for 2^f on [0,1) (max rel. error
+//     8.8e-5 = 2^-13.5, far below the bf16 rounding of P at 2^-9), exponent reinserted with one integer shift-add;
+//   * the row maximum uses 3-input FMNMX3; online softmax never touches O in the common case: the exponent reference m is
+//     only moved when the running row maximum exceeds it by more than 8 (p <= 2^8 stays exact enough in bf16/fp32); only
+//     then the warp rescales its 32 rows of O in TMEM and its row sum.
 #include "common.cuh"
 #include "supir_b200.h"
+
+#include <cstdlib>
 
 namespace supir {
 
 int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
                    const uint32_t* box);
 
-static constexpr int ATT_BM = 128;   // queries per tile (two tiles per CTA)
+static constexpr int ATT_BM = 128;   // queries per tile
 static constexpr int ATT_BN = 128;   // keys per block
 static constexpr int ATT_D = 64;
 static constexpr float ATT_RESCALE_THRESHOLD = 8.0f;   // log2 units
@@ -39,64 +48,165 @@ struct AttnParams {
     __nv_bfloat16* out;
     float scale_log2;
     uint32_t desc_hi;      // smem descriptor template (upper word)
-    uint32_t idesc_qk;     // 128x128, A K-major, B K-major
-    uint32_t idesc_pv;     // 128x64,  A K-major, B MN-major
+    uint32_t idesc_qk;     // 128 x NKEY, A K-major, B K-major
+    uint32_t idesc_pv;     // 128 x 64,  A K-major (TMEM), B MN-major
+    int nqb, num_items;    // query blocks per (batch, head); nqb * H * B work items
 };
 
-// TILES = 128-query tiles per CTA, STAGES = K/V ring depth. <2, 4>: one CTA per SM, two tiles ping-pong (self-attention).
-// <1, 1>: single-block keys (77-token cross-attention): a light CTA (48 KB of shared memory, 256 TMEM columns, 256
-// threads) so that two or three share an SM and one CTA's load / store latency hides behind another's math.
+// ---------------------------------------------------------------------------------------------------------------------
+// packed fp32 pairs (sm_100 FFMA2 / FADD2: two fp32 operations per issue slot)
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t fadd2_rm(uint64_t a, uint64_t b) {   // round towards -inf
+    uint64_t d;
+    asm("add.rm.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// 2^x for a pair, x <= ~100, on the FMA / ALU pipes (no MUFU). x is clamped at -126 (result 2^-126 ~ 0 for anything below,
+// including the -inf of masked keys).
+__device__ __forceinline__ void ex2_emulated_pair(uint64_t x, float& e0, float& e1) {
+    const float kMagic = 12582912.0f;                       // 1.5 * 2^23: x + magic has ulp 1, floor(x) lands in the low mantissa bits
+    float x0, x1;
+    unpack2(x, x0, x1);
+    x0 = fmaxf(x0, -126.0f);
+    x1 = fmaxf(x1, -126.0f);
+    const uint64_t xc = pack2(x0, x1);
+    const uint64_t xr = fadd2_rm(xc, pack2(kMagic, kMagic));            // magic + floor(x)
+    const uint64_t xf = fadd2(xr, pack2(-kMagic, -kMagic));             // floor(x), exact
+    const uint64_t fr = ffma2(xf, pack2(-1.0f, -1.0f), xc);             // x - floor(x) in [0, 1), exact
+    uint64_t p = ffma2(pack2(0.077119089663028717041015625f, 0.077119089663028717041015625f), fr,
+                       pack2(0.227564394474029541015625f, 0.227564394474029541015625f));
+    p = ffma2(p, fr, pack2(0.695146143436431884765625f, 0.695146143436431884765625f));
+    p = ffma2(p, fr, pack2(1.0f, 1.0f));                                // 2^f in [1, 2]
+    float p0, p1, r0, r1;
+    unpack2(p, p0, p1);
+    unpack2(xr, r0, r1);
+    // bits(magic + n) = 0x4B400000 + n: the low 9 bits of the constant are zero, so << 23 leaves n in the exponent field
+    e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(r0) << 23));
+    e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(r1) << 23));
+}
+
+// p = 2^(s * scale - m) for NCOL columns of one row (registers s[]), bf16 pairs to TMEM at tP; returns the row sum of p.
+// EMU of every 4 pairs are evaluated by ex2_emulated_pair, the others on MUFU.
+template <int NCOL, int EMU>
+__device__ __forceinline__ float softmax_row_to_tmem(const uint32_t (&s)[128], float scale_log2, float m_ref, uint32_t tP) {
+    const uint64_t sc2 = pack2(scale_log2, scale_log2), nm2 = pack2(-m_ref, -m_ref);
+    uint64_t ls[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) ls[t] = 0ull;
+#pragma unroll
+    for (int c0 = 0; c0 < NCOL; c0 += 64) {
+        uint32_t pk[32];                                     // 64 probabilities as bf16 pairs
+#pragma unroll
+        for (int i = 0; i < 64; i += 8) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int c = c0 + i + 2 * t;
+                if (c < NCOL) {
+                    const uint64_t x = ffma2(pack2(__uint_as_float(s[c]), __uint_as_float(s[c + 1])), sc2, nm2);
+                    float e0, e1;
+                    // spread the emulated pairs over the group so MUFU and FMA work interleave in the instruction stream
+                    const bool emulate = (EMU == 4) || (EMU == 3 && t != 1) || (EMU == 2 && (t & 1)) || (EMU == 1 && t == 3);
+                    if (emulate) {
+                        ex2_emulated_pair(x, e0, e1);
+                    } else {
+                        float x0, x1;
+                        unpack2(x, x0, x1);
+                        e0 = ex2_approx(x0);
+                        e1 = ex2_approx(x1);
+                    }
+                    ls[t] = fadd2(ls[t], pack2(e0, e1));
+                    pk[(i >> 1) + t] = pack_bf16x2(e0, e1);
+                } else {
+                    pk[(i >> 1) + t] = 0u;
+                }
+            }
+        }
+        tmem_st_32x32(tP + (c0 >> 1), pk);
+    }
+    tmem_st_wait();
+    float a0, a1;
+    unpack2(fadd2(fadd2(ls[0], ls[1]), fadd2(ls[2], ls[3])), a0, a1);
+    return a0 + a1;
+}
+
+// TILES = 128-query tiles per CTA, STAGES = K/V ring depth, NKEY = key columns computed per block (128; 96 when every key
+// fits in 96 rows, i.e. the 77-token text cross-attention), EMU = emulated pairs per 4 (see above).
 template <int TILES, int STAGES>
 struct AttnSmem {
     static constexpr int Q_BYTES = ATT_BM * ATT_D * 2;          // 16 KB per tile
     static constexpr int K_BYTES = ATT_BN * ATT_D * 2;          // 16 KB
     static constexpr int V_BYTES = ATT_BN * ATT_D * 2;          // 16 KB
-    static constexpr int OFF_Q = 0;
-    static constexpr int OFF_K = OFF_Q + TILES * Q_BYTES;
+    static constexpr int OFF_Q = 0;                              // [2 items][TILES]
+    static constexpr int OFF_K = OFF_Q + 2 * TILES * Q_BYTES;
     static constexpr int OFF_V = OFF_K + STAGES * K_BYTES;
     static constexpr int OFF_BAR = OFF_V + STAGES * V_BYTES;
     static constexpr int TOTAL = OFF_BAR + 256 + 1024;
 };
 
-template <int TILES, int STAGES>
+template <int TILES, int STAGES, int NKEY, int EMU>
 __global__ void __launch_bounds__(128 + 128 * TILES, TILES == 1 ? 2 : 1)
 attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-    using AttnSmem = supir::AttnSmem<TILES, STAGES>;
-    constexpr int ATT_STAGES = STAGES;
+    using SM = AttnSmem<TILES, STAGES>;
     constexpr uint32_t TMEM_COLS = TILES == 2 ? 512 : 256;
+    // TMEM columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512) (bf16 pairs)
     constexpr uint32_t COL_O = TILES * ATT_BN, COL_P = TILES * ATT_BN + TILES * ATT_D;
+    constexpr uint32_t KV_TX = (uint32_t)NKEY * ATT_D * 2 * 2;          // bytes of one K + V block as the tensor-map box delivers it
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem + AttnSmem::OFF_Q;
-    uint8_t* sK = smem + AttnSmem::OFF_K;
-    uint8_t* sV = smem + AttnSmem::OFF_V;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnSmem::OFF_BAR);
-    uint64_t* q_full = bars;                // 1
-    uint64_t* kv_full = bars + 1;                       // [ATT_STAGES]
-    uint64_t* kv_empty = kv_full + ATT_STAGES;          // [ATT_STAGES]
-    uint64_t* s_full = kv_empty + ATT_STAGES;           // [2] per tile
+    uint8_t* sQ = smem + SM::OFF_Q;
+    uint8_t* sK = smem + SM::OFF_K;
+    uint8_t* sV = smem + SM::OFF_V;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
+    uint64_t* q_full = bars;                            // [2] per Q buffer
+    uint64_t* q_empty = bars + 2;                       // [2]
+    uint64_t* kv_full = bars + 4;                       // [STAGES]
+    uint64_t* kv_empty = kv_full + STAGES;              // [STAGES]
+    uint64_t* s_full = kv_empty + STAGES;               // [2] per tile
     uint64_t* p_full = s_full + 2;                      // [2] per tile
     uint64_t* pv_done = p_full + 2;                     // [2] per tile
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qblk = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
     const int nblk = (p.Lk + ATT_BN - 1) / ATT_BN;
-    const int q0 = qblk * TILES * ATT_BM;                           // first query row of this CTA (within the batch element)
-    const bool tileB_valid = TILES == 2 && (q0 + ATT_BM) < p.Lq;  // CTA-uniform
+    // work item -> (batch, head, first query row); the same arithmetic in every role. Query blocks of one (batch, head) are
+    // consecutive items, so the CTAs running at the same time share that head's K/V in L2.
+    auto item_q0 = [&](int it) { return (it % p.nqb) * TILES * ATT_BM; };
+    auto item_head = [&](int it) { return (it / p.nqb) % p.H; };
+    auto item_batch = [&](int it) { return it / (p.nqb * p.H); };
+    auto item_tileB = [&](int it) { return TILES == 2 && (item_q0(it) + ATT_BM) < p.Lq; };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ);
         tma_prefetch_desc(&tmK);
         tma_prefetch_desc(&tmV);
-        mbar_init(q_full, 1);
-        for (int s = 0; s < ATT_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
         for (int i = 0; i < 2; ++i) {
+            mbar_init(&q_full[i], 1);
+            mbar_init(&q_empty[i], 1);
             mbar_init(&s_full[i], 1);
             mbar_init(&p_full[i], 4);
             mbar_init(&pv_done[i], 1);
         }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -107,70 +217,105 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
-    // TMEM columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512) (bf16 pairs)
 
     if (warp < 4) {
-      // register budgets: <2,*> 384 threads x 168 -> 56 / 224;  <1,*> 256 threads x 128 (two CTAs per SM) -> 56 / 200
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+      // register budgets: <2,*> 384 threads x 168 -> 64 / 224;  <1,*> 256 threads x 128 (two CTAs per SM) -> 56 / 200
+      if (TILES == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+      else asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
       if (warp == 0) {
         if (lane == 0) {
-            // ---------------- TMA producer ----------------
-            mbar_expect_tx(q_full, (tileB_valid ? 2 : 1) * AttnSmem::Q_BYTES);
-            tma_load_2d(sQ, &tmQ, q_full, head * ATT_D, batch * p.Lq + q0);
-            if (tileB_valid) tma_load_2d(sQ + AttnSmem::Q_BYTES, &tmQ, q_full, head * ATT_D, batch * p.Lq + q0 + ATT_BM);
+            // ---------------- TMA producer: runs ahead of the math by up to one item of Q and STAGES blocks of K/V ----------------
             int stage = 0;
             uint32_t phase = 0;
-            for (int j = 0; j < nblk; ++j) {
-                mbar_wait(&kv_empty[stage], phase ^ 1);
-                mbar_expect_tx(&kv_full[stage], AttnSmem::K_BYTES + AttnSmem::V_BYTES);
-                tma_load_2d(sK + stage * AttnSmem::K_BYTES, &tmK, &kv_full[stage], head * ATT_D, batch * p.Lk + j * ATT_BN);
-                tma_load_2d(sV + stage * AttnSmem::V_BYTES, &tmV, &kv_full[stage], head * ATT_D, batch * p.Lk + j * ATT_BN);
-                if (++stage == ATT_STAGES) { stage = 0; phase ^= 1; }
+            int k = 0;                                                   // local item counter
+            for (int it = blockIdx.x; it < p.num_items; it += gridDim.x, ++k) {
+                const int qi = k & 1;
+                const int head = item_head(it), batch = item_batch(it), q0 = item_q0(it);
+                const bool tb = item_tileB(it);
+                uint8_t* q_buf = sQ + qi * TILES * SM::Q_BYTES;
+                mbar_wait(&q_empty[qi], ((k >> 1) & 1) ^ 1);             // the item that used this buffer two items ago is done with it
+                mbar_expect_tx(&q_full[qi], (tb ? 2 : 1) * SM::Q_BYTES);
+                tma_load_2d(q_buf, &tmQ, &q_full[qi], head * ATT_D, batch * p.Lq + q0);
+                if (tb) tma_load_2d(q_buf + SM::Q_BYTES, &tmQ, &q_full[qi], head * ATT_D, batch * p.Lq + q0 + ATT_BM);
+                for (int j = 0; j < nblk; ++j) {
+                    mbar_wait(&kv_empty[stage], phase ^ 1);
+                    mbar_expect_tx(&kv_full[stage], KV_TX);
+                    tma_load_2d(sK + stage * SM::K_BYTES, &tmK, &kv_full[stage], head * ATT_D, batch * p.Lk + j * ATT_BN);
+                    tma_load_2d(sV + stage * SM::V_BYTES, &tmV, &kv_full[stage], head * ATT_D, batch * p.Lk + j * ATT_BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // ---------------- MMA issuer ----------------
             const uint64_t dtemplate = (uint64_t)p.desc_hi << 32;
-            const int ntile = tileB_valid ? 2 : 1;
-            auto issue_qk = [&](int x, int stage) {
-                const uint64_t qdesc = dtemplate | ((smem_u32(sQ + x * AttnSmem::Q_BYTES) >> 4) & 0x3FFF);
-                const uint64_t kdesc = dtemplate | ((smem_u32(sK + stage * AttnSmem::K_BYTES) >> 4) & 0x3FFF);
+            auto issue_qk = [&](int x, int qi, int stage) {
+                const uint64_t qdesc = dtemplate | ((smem_u32(sQ + (qi * TILES + x) * SM::Q_BYTES) >> 4) & 0x3FFF);
+                const uint64_t kdesc = dtemplate | ((smem_u32(sK + stage * SM::K_BYTES) >> 4) & 0x3FFF);
 #pragma unroll
-                for (int k = 0; k < ATT_D / 16; ++k)
-                    umma_bf16(tmem_base + x * ATT_BN, qdesc + 2 * k, kdesc + 2 * k, p.idesc_qk, k != 0);
+                for (int kk = 0; kk < ATT_D / 16; ++kk)
+                    umma_bf16(tmem_base + x * ATT_BN, qdesc + 2 * kk, kdesc + 2 * kk, p.idesc_qk, kk != 0);
                 umma_commit(&s_full[x]);
             };
-            mbar_wait(q_full, 0);
-            mbar_wait(&kv_full[0], 0);
-            tc_fence_after();
-            for (int x = 0; x < ntile; ++x) issue_qk(x, 0);
-            int stage = 0;                 // stage holding block j
+            int stage = 0;                 // stage holding the current block
             uint32_t kv_phase = 0;
-            for (int j = 0; j < nblk; ++j) {
-                int nstage = stage + 1;
-                uint32_t nphase = kv_phase;
-                if (nstage == ATT_STAGES) { nstage = 0; nphase ^= 1; }
-                if (j + 1 < nblk) {
-                    mbar_wait(&kv_full[nstage], nphase);
-                }
-                for (int x = 0; x < ntile; ++x) {
-                    mbar_wait(&p_full[x], j & 1);       // P_X(j) written, S_X(j) consumed
-                    tc_fence_after();
-                    if (j + 1 < nblk) issue_qk(x, nstage);
-                    const uint32_t vbase = smem_u32(sV + stage * AttnSmem::V_BYTES);
-#pragma unroll
-                    for (int k = 0; k < ATT_BN / 16; ++k) {
-                        // A = P in TMEM: 16 k-elements = 8 columns per step; B = V: MN-major (d contiguous), 16 kv rows of 128 B
-                        const uint32_t va = vbase + k * 16 * 128;
-                        umma_bf16_ts(tmem_base + COL_O + x * ATT_D, tmem_base + COL_P + x * 64 + k * 8,
-                                     dtemplate | ((va >> 4) & 0x3FFF), p.idesc_pv, (j | k) != 0);
+            uint32_t g[2] = {0, 0};        // blocks processed per tile (parity of p_full)
+            int k = 0;
+            if ((int)blockIdx.x < p.num_items) {    // prologue: first QK of the first item
+                mbar_wait(&q_full[0], 0);
+                mbar_wait(&kv_full[0], 0);
+                tc_fence_after();
+                const int nt0 = item_tileB(blockIdx.x) ? 2 : 1;
+                for (int x = 0; x < nt0; ++x) issue_qk(x, 0, 0);
+            }
+            for (int it = blockIdx.x; it < p.num_items; it += gridDim.x, ++k) {
+                const int qi = k & 1;
+                const int ntile = item_tileB(it) ? 2 : 1;
+                const int it_next = it + gridDim.x;
+                const bool more_items = it_next < p.num_items;
+                const int ntile_next = more_items && item_tileB(it_next) ? 2 : 1;
+                for (int j = 0; j < nblk; ++j) {
+                    int nstage = stage + 1;
+                    uint32_t nphase = kv_phase;
+                    if (nstage == STAGES) { nstage = 0; nphase ^= 1; }
+                    const bool last = (j + 1 == nblk);
+                    const bool has_next = !last || more_items;       // a QK to issue ahead: next block, or the next item's first
+                    const int nqi = last ? (qi ^ 1) : qi;
+                    const int nt_next = last ? ntile_next : ntile;   // tiles of the item that owns the next block
+                    if (has_next) {
+                        if (last) mbar_wait(&q_full[nqi], ((k + 1) >> 1) & 1);
+                        mbar_wait(&kv_full[nstage], nphase);
                     }
-                    umma_commit(&pv_done[x]);
+                    for (int x = 0; x < TILES; ++x) {
+                        const bool cur = x < ntile, nxt = has_next && x < nt_next;
+                        if (cur) {
+                            mbar_wait(&p_full[x], g[x] & 1);     // P_X of this block written, S_X consumed
+                            tc_fence_after();
+                        }
+                        // tile B may sit out an item (ragged last query block): its S is then free already
+                        if (nxt) {
+                            if (!cur) tc_fence_after();
+                            issue_qk(x, nqi, nstage);
+                        }
+                        if (cur) {
+                            const uint32_t vbase = smem_u32(sV + stage * SM::V_BYTES);
+#pragma unroll
+                            for (int kk = 0; kk < NKEY / 16; ++kk) {
+                                // A = P in TMEM: 16 k-elements = 8 columns per step; B = V: MN-major (d contiguous), 16 kv rows of 128 B
+                                const uint32_t va = vbase + kk * 16 * 128;
+                                umma_bf16_ts(tmem_base + COL_O + x * ATT_D, tmem_base + COL_P + x * 64 + kk * 8,
+                                             dtemplate | ((va >> 4) & 0x3FFF), p.idesc_pv, (j | kk) != 0);
+                            }
+                            umma_commit(&pv_done[x]);
+                            ++g[x];
+                        }
+                    }
+                    umma_commit(&kv_empty[stage]);
+                    if (last) umma_commit(&q_empty[qi]);            // every QK of this item was issued before this point
+                    stage = nstage;
+                    kv_phase = nphase;
                 }
-                umma_commit(&kv_empty[stage]);
-                stage = nstage;
-                kv_phase = nphase;
             }
         }
       }
@@ -179,44 +324,48 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         else asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
         // ---------------- softmax / output warps ----------------
         const int x = (warp - 4) >> 2;                          // tile 0 (A) or 1 (B)
-        if (x == 0 || tileB_valid) {
-            const int quad = warp & 3;
-            const int row = quad * 32 + lane;                   // query row inside the tile
-            const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-            const uint32_t tS = tmem_base + x * ATT_BN + lane_off;
-            const uint32_t tO = tmem_base + COL_O + x * ATT_D + lane_off;
-            const uint32_t tP = tmem_base + COL_P + x * 64 + lane_off;
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;                       // query row inside the tile
+        const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+        const uint32_t tS = tmem_base + x * ATT_BN + lane_off;
+        const uint32_t tO = tmem_base + COL_O + x * ATT_D + lane_off;
+        const uint32_t tP = tmem_base + COL_P + x * 64 + lane_off;
+        uint32_t g = 0;                                         // blocks processed by this tile (barrier parities)
+        for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
+            if (x == 1 && !item_tileB(it)) continue;
+            const int head = item_head(it), batch = item_batch(it), q0 = item_q0(it);
             float m_ref = 0.f, l_run = 0.f;
-            for (int j = 0; j < nblk; ++j) {
-                mbar_wait(&s_full[x], j & 1);
+            for (int j = 0; j < nblk; ++j, ++g) {
+                mbar_wait(&s_full[x], g & 1);
                 tc_fence_after();
                 uint32_t s[128];
                 tmem_ld_32x32_at<0>(tS + 0, s);
                 tmem_ld_32x32_at<32>(tS + 32, s);
                 tmem_ld_32x32_at<64>(tS + 64, s);
-                tmem_ld_32x32_at<96>(tS + 96, s);
+                if (NKEY > 96) tmem_ld_32x32_at<96>(tS + 96, s);
                 tmem_ld_wait();
                 const int kv_valid = min(ATT_BN, p.Lk - j * ATT_BN);
-                if (kv_valid != ATT_BN) {
+                if (kv_valid < NKEY) {
 #pragma unroll
-                    for (int i = 0; i < 128; ++i)
+                    for (int i = 0; i < NKEY; ++i)
                         if (i >= kv_valid) s[i] = 0xff800000u;   // -inf
                 }
-                // row maximum with 8 independent chains (a single chain would serialise 128 dependent FMNMX)
+                // row maximum with 8 independent chains (FMNMX3 pairs them up); a single chain would serialise
                 float mxa[8];
 #pragma unroll
                 for (int t = 0; t < 8; ++t) mxa[t] = __uint_as_float(s[t]);
 #pragma unroll
-                for (int i = 8; i < 128; i += 8) {
+                for (int i = 8; i < NKEY; i += 8) {
 #pragma unroll
                     for (int t = 0; t < 8; ++t) mxa[t] = fmaxf(mxa[t], __uint_as_float(s[i + t]));
                 }
                 float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])),
                                  fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
                 mx *= p.scale_log2;
-                // previous PV of this tile must have finished: it reads P (about to be overwritten) and updates O
-                if (j > 0) {
-                    mbar_wait(&pv_done[x], (j - 1) & 1);
+                // the previous PV of this tile (possibly the previous item's last) reads P, which is about to be overwritten,
+                // and updates O, which a rescale would touch
+                if (g > 0) {
+                    mbar_wait(&pv_done[x], (g - 1) & 1);
                     tc_fence_after();
                 }
                 if (j == 0) {
@@ -239,33 +388,13 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                         tmem_st_wait();
                     }
                 }
-                float ls[8];
-#pragma unroll
-                for (int t = 0; t < 8; ++t) ls[t] = 0.f;
-#pragma unroll
-                for (int c0 = 0; c0 < ATT_BN; c0 += 64) {
-                    uint32_t pk[32];                                     // 64 probabilities as bf16 pairs
-#pragma unroll
-                    for (int i = 0; i < 64; i += 8) {
-                        float e[8];
-#pragma unroll
-                        for (int t = 0; t < 8; ++t) {
-                            e[t] = ex2_approx(fmaf(__uint_as_float(s[c0 + i + t]), p.scale_log2, -m_ref));
-                            ls[t] += e[t];
-                        }
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) pk[(i >> 1) + t] = pack_bf16x2(e[2 * t], e[2 * t + 1]);
-                    }
-                    tmem_st_32x32(tP + (c0 >> 1), pk);
-                }
-                tmem_st_wait();
-                l_run += ((ls[0] + ls[1]) + (ls[2] + ls[3])) + ((ls[4] + ls[5]) + (ls[6] + ls[7]));
+                l_run += softmax_row_to_tmem<NKEY, EMU>(s, p.scale_log2, m_ref, tP);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&p_full[x]);
             }
-            // epilogue: O / l
-            mbar_wait(&pv_done[x], (nblk - 1) & 1);
+            // epilogue of the item: O / l. The next item's first QK for this tile is already in flight.
+            mbar_wait(&pv_done[x], (g - 1) & 1);
             tc_fence_after();
             const int qrow = q0 + x * ATT_BM + row;
             const float inv = 1.f / l_run;
@@ -287,6 +416,8 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     }
                 }
             }
+            // O of this tile is read: order the TMEM loads before the P write / arrive that lets the next item's PV overwrite it
+            tc_fence_before();
         }
     }
 
@@ -300,21 +431,51 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
 static long long g_att_desc_override = -1;
 static long long g_att_idesc_pv_override = -1;
+static int g_att_emu = -1;            // emulated exponent pairs per 4: -1 = environment / default
 
-template <int TILES, int STAGES>
-static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnParams& p, int B,
+static int attention_emu() {
+    if (g_att_emu < 0) {
+        const char* e = getenv("SUPIR_B200_ATTN_EMU");
+        g_att_emu = e ? atoi(e) : 2;
+        if (g_att_emu < 0 || g_att_emu > 4) g_att_emu = 2;
+    }
+    return g_att_emu;
+}
+
+template <int TILES, int STAGES, int NKEY, int EMU>
+static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, AttnParams p, int B,
                             cudaStream_t st) {
     using S = AttnSmem<TILES, STAGES>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        SUPIR_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<TILES, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-        attr_set = true;
+    // function attributes are per device: set them once for every device this process launches on
+    static bool attr_set[64] = {};
+    int dev = 0;
+    SUPIR_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        SUPIR_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<TILES, STAGES, NKEY, EMU>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    dim3 grid((p.Lq + TILES * ATT_BM - 1) / (TILES * ATT_BM), p.H, B);
-    attention_d64_kernel<TILES, STAGES><<<grid, 128 + 128 * TILES, S::TOTAL, st>>>(tmQ, tmK, tmV, p);
+    p.nqb = (p.Lq + TILES * ATT_BM - 1) / (TILES * ATT_BM);
+    p.num_items = p.nqb * p.H * B;
+    p.idesc_qk = umma_idesc_bf16(ATT_BM, NKEY, 0, 0);
+    const int slots = device_sm_count() * (TILES == 1 ? 2 : 1);
+    const int grid = p.num_items < slots ? p.num_items : slots;
+    attention_d64_kernel<TILES, STAGES, NKEY, EMU><<<grid, 128 + 128 * TILES, S::TOTAL, st>>>(tmQ, tmK, tmV, p);
     count_launch();
     SUPIR_CHECK_CUDA(cudaGetLastError());
     return SUPIR_OK;
+}
+
+template <int TILES, int STAGES, int NKEY>
+static int launch_attention_emu(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnParams& p, int B,
+                                cudaStream_t st) {
+    switch (attention_emu()) {
+        case 0: return launch_attention<TILES, STAGES, NKEY, 0>(tmQ, tmK, tmV, p, B, st);
+        case 1: return launch_attention<TILES, STAGES, NKEY, 1>(tmQ, tmK, tmV, p, B, st);
+        case 3: return launch_attention<TILES, STAGES, NKEY, 3>(tmQ, tmK, tmV, p, B, st);
+        case 4: return launch_attention<TILES, STAGES, NKEY, 4>(tmQ, tmK, tmV, p, B, st);
+        default: return launch_attention<TILES, STAGES, NKEY, 2>(tmQ, tmK, tmV, p, B, st);
+    }
 }
 
 }  // namespace supir
@@ -327,22 +488,30 @@ extern "C" int supir_debug_set_attention_descriptors(long long smem_desc_templat
     return SUPIR_OK;
 }
 
+extern "C" int supir_set_attention_exp_emulation(int pairs_of_4) {
+    g_att_emu = pairs_of_4 < 0 ? -1 : (pairs_of_4 > 4 ? 4 : pairs_of_4);
+    return SUPIR_OK;
+}
+
 extern "C" int supir_attention_bf16(const void* q, long long ldq, const void* k, long long ldk, const void* v,
                                     long long ldv, void* out, long long ldo, int B, int H, int Lq, int Lk, int head_dim,
                                     float scale, void* stream) {
     SUPIR_REQUIRE(q && k && v && out, "supir_attention_bf16: null pointer");
-    SUPIR_REQUIRE(head_dim == 64, "supir_attention_bf16: head_dim %d unsupported (64 only)", head_dim);
+    SUPIR_REQUIRE(head_dim == 64, "supir_attention_bf16: head_dim %d unsupported (64 only; the VAE's single 512-wide head is supir_attention_d512_bf16)", head_dim);
     SUPIR_REQUIRE(B > 0 && H > 0 && Lq > 0 && Lk > 0, "supir_attention_bf16: bad shape");
+    SUPIR_REQUIRE(scale > 0.f, "supir_attention_bf16: scale must be positive");
     SUPIR_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "supir_attention_bf16: leading dims must be multiples of 8");
+    const bool short_keys = Lk <= 96;          // 77-token text context: 96 key columns per block instead of 128
     CUtensorMap tmQ, tmK, tmV;
-    const uint32_t box[2] = {ATT_D, ATT_BM};
     int rc;
     {
+        const uint32_t box[2] = {ATT_D, ATT_BM};
         const uint64_t dims[2] = {(uint64_t)H * ATT_D, (uint64_t)B * Lq};
         const uint64_t str[1] = {(uint64_t)ldq};
         if ((rc = make_tmap_bf16(&tmQ, q, 2, dims, str, box))) return rc;
     }
     {
+        const uint32_t box[2] = {ATT_D, (uint32_t)(short_keys ? 96 : ATT_BN)};
         const uint64_t dims[2] = {(uint64_t)H * ATT_D, (uint64_t)B * Lk};
         const uint64_t str[1] = {(uint64_t)ldk};
         if ((rc = make_tmap_bf16(&tmK, k, 2, dims, str, box))) return rc;
@@ -357,11 +526,11 @@ extern "C" int supir_attention_bf16(const void* q, long long ldq, const void* k,
     const uint64_t dt = g_att_desc_override >= 0 ? (uint64_t)g_att_desc_override
                                                  : (((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61));
     p.desc_hi = (uint32_t)(dt >> 32);
-    p.idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN, 0, 0);
     p.idesc_pv = g_att_idesc_pv_override >= 0 ? (uint32_t)g_att_idesc_pv_override : umma_idesc_bf16(ATT_BM, ATT_D, 0, 1);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    // one key block (77-token cross-attention): light one-tile CTAs, two per SM. One-tile CTAs measured no better than the
-    // two-tile kernel for multi-block self-attention (745 vs 762 TFLOP/s at 4096 tokens), so that keeps the ping-pong.
-    if (Lk <= ATT_BN) return launch_attention<1, 1>(tmQ, tmK, tmV, p, B, st);
-    return launch_attention<2, 4>(tmQ, tmK, tmV, p, B, st);
+    // one key block (77-token cross-attention, small ZeroCrossAttn contexts): light one-tile CTAs, two per SM, so one CTA's
+    // load / store latency hides behind the other's math; longer keys: two tiles ping-pong inside one CTA per SM.
+    if (short_keys) return launch_attention_emu<1, 2, 96>(tmQ, tmK, tmV, p, B, st);
+    if (Lk <= ATT_BN) return launch_attention_emu<1, 2, 128>(tmQ, tmK, tmV, p, B, st);
+    return launch_attention_emu<2, 4, 128>(tmQ, tmK, tmV, p, B, st);
 }

@@ -77,6 +77,21 @@ class _Level(nn.Module):
 class _VAENet(nn.Module):
     is_decoder = False
 
+    def __init__(self):
+        super().__init__()
+        self._packed, self._pool = False, None
+        # kernel-layout weights are derived data: a later load_state_dict (gradio_demo*.py switch the Q / F checkpoints at
+        # run time) or .to() must re-pack them, like ControlWrapper does for the diffusion networks
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate())
+
+    def invalidate(self):
+        self._packed, self._pool = False, None
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        self.invalidate()
+        return r
+
     # ---- packing: per-step kernel-layout weights ----
     def pack(self):
         self._steps = []

@@ -377,6 +377,15 @@ static bool test_attention(int B, int H, int Lq, int Lk, int sample_rows) {
     return ok;
 }
 
+// pseudo-random bf16 fill (hash of the index, roughly uniform in [-amp, amp]): realistic operand toggling for power / timing
+__global__ void fill_random_bf16(__nv_bfloat16* p, size_t n, float amp, uint32_t seed) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t h = (uint32_t)i * 2654435761u ^ seed;
+        h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+        p[i] = __float2bfloat16_rn(((h >> 8) * (1.0f / 8388608.0f) - 1.0f) * amp);
+    }
+}
+
 static void perf_attention(int B, int H, int Lq, int Lk) {
     const int C = H * 64;
     __nv_bfloat16 *dQ, *dK, *dV, *dO;
@@ -384,9 +393,9 @@ static void perf_attention(int B, int H, int Lq, int Lk) {
     CK(cudaMalloc(&dK, (size_t)B * Lk * C * 2));
     CK(cudaMalloc(&dV, (size_t)B * Lk * C * 2));
     CK(cudaMalloc(&dO, (size_t)B * Lq * C * 2));
-    CK(cudaMemset(dQ, 0x11, (size_t)B * Lq * C * 2));
-    CK(cudaMemset(dK, 0x11, (size_t)B * Lk * C * 2));
-    CK(cudaMemset(dV, 0x11, (size_t)B * Lk * C * 2));
+    fill_random_bf16<<<1024, 256>>>(dQ, (size_t)B * Lq * C, 2.0f, 1u);
+    fill_random_bf16<<<1024, 256>>>(dK, (size_t)B * Lk * C, 2.0f, 2u);
+    fill_random_bf16<<<1024, 256>>>(dV, (size_t)B * Lk * C, 1.0f, 3u);
     for (int i = 0; i < 3; ++i) supir_attention_bf16(dQ, C, dK, C, dV, C, dO, C, B, H, Lq, Lk, 64, 0.125f, nullptr);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -558,6 +567,9 @@ int main(int argc, char** argv) {
         supir_set_gemm_pair_mode(1);
     }
     if (what == "attn" || what == "all") {
+      for (int emu : {0, 2, 4}) {
+        printf("-- softmax exponent emulation %d of 4 pairs\n", emu);
+        supir_set_attention_exp_emulation(emu);
         test_attention(1, 1, 128, 128, 0);
         test_attention(1, 2, 128, 256, 0);
         test_attention(2, 3, 200, 77, 0);
@@ -565,6 +577,11 @@ int main(int argc, char** argv) {
         test_attention(2, 10, 1024, 1024, 2000);
         test_attention(2, 20, 4096, 4096, 500);
         test_attention(2, 10, 4096, 77, 2000);
+        test_attention(3, 2, 700, 96, 0);
+        test_attention(3, 2, 300, 128, 0);
+        test_attention(40, 20, 1024, 1024, 300);      // more work items than SMs: the persistent loop wraps
+      }
+      supir_set_attention_exp_emulation(-1);
     }
     if (what == "attnperf" || what == "all") {
         perf_attention(2, 10, 4096, 4096);
@@ -573,11 +590,16 @@ int main(int argc, char** argv) {
         perf_attention(2, 10, 4096, 77);
         perf_attention(2, 20, 1024, 77);
     }
-    if (what == "attnperf2") {   // the shapes of the 49-window step (batch 98)
-        perf_attention(98, 10, 4096, 4096);
-        perf_attention(98, 20, 1024, 1024);
-        perf_attention(98, 10, 4096, 77);
-        perf_attention(98, 20, 1024, 77);
+    if (what == "attnperf2") {   // the shapes of the 49-window step (batch 98), for every exponent-emulation setting
+        for (int emu = 0; emu <= 4; ++emu) {
+            printf("-- softmax exponent emulation %d of 4 pairs\n", emu);
+            supir_set_attention_exp_emulation(emu);
+            perf_attention(98, 10, 4096, 4096);
+            perf_attention(98, 20, 1024, 1024);
+            perf_attention(98, 10, 4096, 77);
+            perf_attention(98, 20, 1024, 77);
+        }
+        supir_set_attention_exp_emulation(-1);
     }
     if (what == "sanitize") {   // small cases for compute-sanitizer (memcheck / racecheck / synccheck)
         for (int bn : {0, 64, 160}) {
