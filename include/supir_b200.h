@@ -59,6 +59,10 @@ int supir_set_gemm_tile_n(int bn);
  * each CTA staging half of the W tile). 0 = single-CTA kernel everywhere, 1 = pairs where they measured faster (default;
  * also settable through the environment variable SUPIR_B200_GEMM_PAIR), 2 = pairs whenever the tile is 256 wide */
 int supir_set_gemm_pair_mode(int on);
+/* tuning knob for the staged epilogue: 0 = one TMA load / store per 128-row chunk, issued by one thread of each 4-warp group
+ * behind two named barriers (default); 1 = every epilogue warp moves its own 32 rows with its own TMA operations and
+ * mbarriers, no cross-warp barrier in the chunk loop; negative = environment (SUPIR_B200_GEMM_WARP_EPILOGUE) / default. */
+int supir_set_gemm_epilogue_mode(int per_warp);
 /* debugging: 1 routes every GEMM through the direct-store epilogue instead of the shared-memory + TMA-store one */
 int supir_debug_force_direct_epilogue(int on);
 /* debugging: override the UMMA shared-memory descriptor template / instruction descriptor (-1 = built-in default) */

@@ -23,6 +23,7 @@ _SIGS = {
     "supir_conv3x3_bf16": [c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(Epilogue), c_void_p],
     "supir_set_gemm_tile_n": [c_int],
     "supir_set_gemm_pair_mode": [c_int],
+    "supir_set_gemm_epilogue_mode": [c_int],
     "supir_debug_force_direct_epilogue": [c_int],
     "supir_debug_set_umma_descriptors": [c_ll, c_ll],
     "supir_conv3x3_small_cin": [c_void_p, c_ll, c_ll, c_ll, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_void_p],

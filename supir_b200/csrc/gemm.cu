@@ -56,6 +56,7 @@ struct GemmKernelParams {
     int nimg;             // conv mode: number of images (patches beyond it are padding of the last CTA pair)
     int staged;           // 1: epilogue through shared memory (bias tile in smem, TMA-loaded residual, TMA store)
     int has_res;          // staged path: residual tensor map valid
+    int warp_epi;         // staged path: 1 = every epilogue warp moves ITS 32 rows with its own TMA operations (no named barriers)
     uint32_t desc_hi;     // upper 32 bits of the shared-memory matrix descriptor (SBO / version / swizzle mode)
     uint32_t desc_lbo;    // LBO field (bits 16..29 of the low word), pre-shifted
     uint32_t idesc;       // tcgen05 instruction descriptor
@@ -73,7 +74,7 @@ struct GemmSmem {
     static constexpr int EPI_BYTES = 8 * CH_BYTES + 2 * BN * 4;
     static constexpr int ACC_STRIDE = (BN == 160) ? 256 : BN;          // TMEM column offset of the second accumulator
     static constexpr int TMEM_COLS = (BN == 160) ? 512 : 2 * BN;       // allocation must be a power of two
-    static constexpr int BAR_BYTES = 256;
+    static constexpr int BAR_BYTES = 512;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
 };
 
@@ -99,8 +100,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint64_t* empty_bar = bars + STAGES;          // [STAGES]
     uint64_t* tmem_full = bars + 2 * STAGES;      // [2]
     uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]
-    uint64_t* res_full = bars + 2 * STAGES + 4;   // [2 half-groups][2 buffers]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
+    uint64_t* res_full = bars + 2 * STAGES + 4;   // [8 epilogue warps][2 buffers] (group mode uses [2 half-groups][2 buffers])
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 20);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -117,7 +118,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_init(&tmem_full[a], 1);
             mbar_init(&tmem_empty[a], 8 * CTAS);  // one arrive per epilogue warp (of both CTAs of a pair)
         }
-        for (int a = 0; a < 4; ++a) mbar_init(&res_full[a], 1);
+        for (int a = 0; a < 16; ++a) mbar_init(&res_full[a], 1);
         if (p.staged) {
             tma_prefetch_desc(&tmC);
             if (p.has_res) tma_prefetch_desc(&tmR);
@@ -218,16 +219,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // half-group h = 4 warps = all 128 accumulator rows; it owns the 32-column chunks c = h, h+2, ... of the tile.
         // Per chunk: TMEM -> registers (+bias, activation, +residual read from a TMA-loaded smem tile) -> bf16 -> swizzled
         // smem -> one TMA store. Global traffic is whole lines moved by the TMA engine; the LSU only sees shared memory.
+        // warp_epi mode: every warp loads / stores ITS 32 rows of the chunk with its own TMA operations (32-row boxes) and
+        // mbarriers, so the chunk loop has no cross-warp barrier at all.
         const int quad = warp & 3;
         const int h = (warp - 2) >> 2;
         const int row = quad * 32 + lane;                          // accumulator row = TMEM lane
-        const bool elected = (warp == 2 + 4 * h) && lane == 0;
+        const bool wl = p.warp_epi != 0;
+        const bool elected = wl ? (lane == 0) : ((warp == 2 + 4 * h) && lane == 0);
+        const int sub = wl ? quad * 32 : 0;                        // first row this thread's TMA operations cover in the chunk buffers
+        const uint32_t res_bytes = wl ? 32 * 64 : BM * 64;
         const int epi_tid = (warp - 2) * 32 + lane;                // 0..255
         const bool geglu = p.act == 2;
         uint8_t* stage_c = smem_epi + h * 2 * S::CH_BYTES;
         uint8_t* stage_r = smem_epi + 4 * S::CH_BYTES + h * 2 * S::CH_BYTES;
         float* s_bias = reinterpret_cast<float*>(smem_epi + 8 * S::CH_BYTES);
-        uint64_t* my_res_full = res_full + 2 * h;
+        uint64_t* my_res_full = res_full + (wl ? 2 * (warp - 2) : 2 * h);
         // swizzled 16-byte chunk position inside a staging row (64B swizzle for 64-byte rows, 32B swizzle for GEGLU's 32-byte rows)
         const int row_bytes = geglu ? 32 : 64;
         const int sw = geglu ? ((row >> 2) & 1) : ((row >> 1) & 3);
@@ -253,10 +259,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             nvalid = nvalid > NCH ? NCH : nvalid;
             const int nck = nvalid > h ? (nvalid - h + 1) / 2 : 0;
             auto out_col = [&](int k) { const int n0 = nt * BN + (h + 2 * k) * 32; return geglu ? (n0 >> 1) : n0; };
+            // rows covered by this thread's TMA operations: the whole 128-row chunk, or (warp_epi) this warp's 32 rows =
+            // rows [rt*128 + sub, +32) of the matrix / pixels [sub, sub+32) of the TH x TW patch
+            const int sx = p.conv ? cx0 + sub % p.TW : 0, sy = p.conv ? cy0 + sub / p.TW : 0;
             auto issue_res = [&](int k, int buf) {
-                mbar_expect_tx(&my_res_full[buf], BM * 64);
-                if (p.conv) tma_load_4d(stage_r + buf * S::CH_BYTES, &tmR, &my_res_full[buf], out_col(k), cx0, cy0, cb);
-                else tma_load_2d(stage_r + buf * S::CH_BYTES, &tmR, &my_res_full[buf], out_col(k), rt * BM);
+                mbar_expect_tx(&my_res_full[buf], res_bytes);
+                uint8_t* dst = stage_r + buf * S::CH_BYTES + sub * 64;
+                if (p.conv) tma_load_4d(dst, &tmR, &my_res_full[buf], out_col(k), sx, sy, cb);
+                else tma_load_2d(dst, &tmR, &my_res_full[buf], out_col(k), rt * BM + sub);
             };
             // tile prologue: bias (+ per-image vector) for the tile's columns; first two residual chunks
             float* sb = s_bias + acc * BN;
@@ -333,7 +343,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 // the TMA store issued two chunks ago read this staging buffer: make sure it is done, tell the group
                 if (elected) bulk_wait_group_read<1>();
-                named_bar_sync(1 + h, 128);
+                if (wl) __syncwarp(); else named_bar_sync(1 + h, 128);
                 uint8_t* crow = stage_c + buf * S::CH_BYTES + row * row_bytes;
                 if (geglu) {
                     *reinterpret_cast<uint4*>(crow + ((0 ^ sw) << 4)) = q[0];
@@ -343,10 +353,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     for (int j4 = 0; j4 < 4; ++j4) *reinterpret_cast<uint4*>(crow + ((j4 ^ sw) << 4)) = q[j4];
                 }
                 fence_proxy_async_smem();
-                named_bar_sync(1 + h, 128);
+                if (wl) __syncwarp(); else named_bar_sync(1 + h, 128);
                 if (elected) {
-                    if (p.conv) tma_store_4d(&tmC, stage_c + buf * S::CH_BYTES, out_col(k), cx0, cy0, cb);
-                    else tma_store_2d(&tmC, stage_c + buf * S::CH_BYTES, out_col(k), rt * BM);
+                    const uint8_t* src = stage_c + buf * S::CH_BYTES + sub * row_bytes;
+                    if (p.conv) tma_store_4d(&tmC, src, out_col(k), sx, sy, cb);
+                    else tma_store_2d(&tmC, src, out_col(k), rt * BM + sub);
                     bulk_commit_group();
                     if (p.has_res && k + 2 < nck) issue_res(k + 2, buf);
                 }
@@ -717,6 +728,14 @@ long long g_desc_override = -1;   // debug: full 64-bit descriptor template (add
 long long g_idesc_override = -1;  // debug: instruction descriptor, -1 = default
 
 int g_force_direct_epilogue = 0;   // debug: 1 disables the staged (smem + TMA store) epilogue
+int g_warp_epilogue = -1;          // staged epilogue: 0 = one TMA op per 128-row chunk (named barriers), 1 = per-warp 32-row TMA ops; -1 = env/default
+static int gemm_epilogue_mode() {
+    if (g_warp_epilogue < 0) {
+        const char* e = getenv("SUPIR_B200_GEMM_WARP_EPILOGUE");
+        g_warp_epilogue = e ? (atoi(e) != 0) : 0;
+    }
+    return g_warp_epilogue;
+}
 
 // staged epilogue applies to bf16 outputs with 16-byte aligned rows; it needs the per-image vector to be uniform per tile
 static bool can_stage(const GemmKernelParams& p) {
@@ -735,7 +754,9 @@ static int make_epi_maps(const GemmKernelParams& p, CUtensorMap* tmC, CUtensorMa
     int rc;
     if (p.conv) {
         const uint64_t dims[4] = {(uint64_t)p.n_out, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)(p.M / ((long long)p.H * p.W))};
-        const uint32_t box[4] = {cols, (uint32_t)p.TW, (uint32_t)p.TH, 1};
+        const uint32_t bw = p.TW < 32 ? p.TW : 32;                      // warp_epi: one warp's 32 pixels of the TH x TW patch
+        const uint32_t box_full[4] = {cols, (uint32_t)p.TW, (uint32_t)p.TH, 1}, box_warp[4] = {cols, bw, 32 / bw, 1};
+        const uint32_t* box = p.warp_epi ? box_warp : box_full;
         const uint64_t sc[3] = {(uint64_t)p.ldc, (uint64_t)p.ldc * p.W, (uint64_t)p.ldc * p.W * p.H};
         if ((rc = make_tmap_bf16_sw(tmC, p.out, 4, dims, sc, box, sw))) return rc;
         if (p.residual) {
@@ -744,7 +765,7 @@ static int make_epi_maps(const GemmKernelParams& p, CUtensorMap* tmC, CUtensorMa
         }
     } else {
         const uint64_t dims[2] = {(uint64_t)p.n_out, (uint64_t)p.M};
-        const uint32_t box[2] = {cols, (uint32_t)BM};
+        const uint32_t box[2] = {cols, (uint32_t)(p.warp_epi ? 32 : BM)};
         const uint64_t sc[1] = {(uint64_t)p.ldc};
         if ((rc = make_tmap_bf16_sw(tmC, p.out, 2, dims, sc, box, sw))) return rc;
         if (p.residual) {
@@ -759,6 +780,7 @@ static int run_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmKernelPa
     CUtensorMap tmC = tmA, tmR = tmA;   // placeholders when the direct epilogue is used
     p.staged = can_stage(p) ? 1 : 0;
     p.has_res = (p.staged && p.residual) ? 1 : 0;
+    p.warp_epi = (p.staged && gemm_epilogue_mode()) ? 1 : 0;
     if (p.staged) {
         const int rc = make_epi_maps(p, &tmC, &tmR);
         if (rc) return rc;
@@ -810,6 +832,11 @@ extern "C" int supir_debug_set_umma_descriptors(long long smem_desc_template, lo
 
 extern "C" int supir_debug_force_direct_epilogue(int on) {
     g_force_direct_epilogue = on;
+    return SUPIR_OK;
+}
+
+extern "C" int supir_set_gemm_epilogue_mode(int per_warp) {
+    g_warp_epilogue = per_warp < 0 ? -1 : (per_warp != 0);
     return SUPIR_OK;
 }
 

@@ -50,6 +50,7 @@ class SUPIRModel(nn.Module):
         self.ae_dtype = {"fp32": torch.float32, "bf16": torch.bfloat16}[ae_dtype]
         self.model.dtype = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}[diffusion_dtype]
         self.p_p, self.n_p = p_p, n_p
+        self._shard_group, self._shard = None, False
 
     # ---- first stage (SUPIR_model.py:41-69) ----
     @torch.no_grad()
@@ -77,6 +78,23 @@ class SUPIRModel(nn.Module):
         for net, size, dec in ((fs.denoise_encoder, encoder_tile_size, False), (fs.encoder, encoder_tile_size, False),
                                (fs.decoder, decoder_tile_size, True)):
             net.forward = VAEHook(net, size, is_decoder=dec, fast_decoder=False, fast_encoder=False, color_fix=False, to_gpu=True)
+            net.forward.shard, net.forward.process_group = self._shard, self._shard_group
+
+    def enable_tile_sharding(self, process_group=None, enabled=True):
+        """Opt in to sharding ONE image's sampler windows and VAE tiles over the ranks of `process_group` (default: the
+        world group). Every rank must call batchify_sample with the same inputs; the seed is broadcast from rank 0 so
+        `noised_z` and the per-step noise agree. Without this call torch.distributed is never touched (a data-parallel
+        caller with different images per rank is safe)."""
+        self._shard, self._shard_group = bool(enabled), process_group
+        fs = self.first_stage_model
+        for net in (fs.denoise_encoder, fs.encoder, fs.decoder, getattr(fs, "denoise_encoder_s1", None)):
+            hook = getattr(net, "forward", None) if net is not None else None
+            if isinstance(hook, VAEHook):
+                hook.shard, hook.process_group = self._shard, process_group
+
+    def _sharded_world(self):
+        import torch.distributed as dist
+        return self._shard and dist.is_available() and dist.is_initialized() and dist.get_world_size(self._shard_group) > 1
 
     # ---- sampling (SUPIR_model.py:79-136) ----
     def make_sampler(self, num_steps, restoration_scale, s_churn, s_noise, cfg_scale, use_linear_CFG, cfg_scale_start):
@@ -87,7 +105,10 @@ class SUPIRModel(nn.Module):
         g["scale_min"] = cfg_scale
         g["scale"] = cfg_scale_start if use_linear_CFG else cfg_scale
         params["restore_cfg"], params["s_churn"], params["s_noise"] = restoration_scale, s_churn, s_noise
-        return instantiate_from_config(cfg)
+        smp = instantiate_from_config(cfg)
+        if hasattr(smp, "shard"):
+            smp.shard, smp.process_group = self._shard, self._shard_group
+        return smp
 
     def prepare_condition(self, _z, p, p_p, n_p, N):
         if self.conditioner is None:
@@ -99,8 +120,20 @@ class SUPIRModel(nn.Module):
                  "aesthetic_score": torch.tensor([9.0]).repeat(N, 1).to(_z.device), "control": _z}
         batch_uc = copy.deepcopy(batch)
         batch_uc["txt"] = [n_p for _ in p]
-        batch["txt"] = ["".join([_p, p_p]) for _p in p]
-        return self.conditioner.get_unconditional_conditioning(batch, batch_uc)
+        if not isinstance(p[0], list):
+            batch["txt"] = ["".join([_p, p_p]) for _p in p]
+            return self.conditioner.get_unconditional_conditioning(batch, batch_uc)
+        # local prompts: one conditioning per sampler window (SUPIR_model.py:163-176)
+        assert len(p) == 1, "Support bs=1 only for local prompt conditioning."
+        c, uc = [], None
+        for i, p_tile in enumerate(p[0]):
+            batch["txt"] = ["".join([p_tile, p_p])]
+            if i == 0:
+                _c, uc = self.conditioner.get_unconditional_conditioning(batch, batch_uc)
+            else:
+                _c, _ = self.conditioner.get_unconditional_conditioning(batch, None)
+            c.append(_c)
+        return c, uc
 
     @torch.no_grad()
     def batchify_sample(self, x, p=None, p_p="default", n_p="default", num_steps=100, restoration_scale=4.0, s_churn=0,
@@ -118,6 +151,12 @@ class SUPIRModel(nn.Module):
         self.sampler = self.make_sampler(num_steps, restoration_scale, s_churn, s_noise, cfg_scale, use_linear_CFG, cfg_scale_start)
         if seed == -1:
             seed = random.randint(0, 65535)
+        if self._sharded_world():         # all ranks of a sharded run must draw the same noise: rank 0's seed wins
+            import torch.distributed as dist
+            box = [seed]
+            dist.broadcast_object_list(box, src=dist.get_global_rank(self._shard_group, 0) if self._shard_group is not None else 0,
+                                       group=self._shard_group)
+            seed = int(box[0])
         random.seed(seed)
         torch.manual_seed(seed)
         _z = self.encode_first_stage_with_denoise(x, use_sample=False)
@@ -126,7 +165,12 @@ class SUPIRModel(nn.Module):
         if c is None:
             c, uc = self.prepare_condition(_z, p, self.p_p if p_p == "default" else p_p, self.n_p if n_p == "default" else n_p, N)
         else:
-            c, uc = dict(c, control=_z), dict(uc, control=_z)
+            def with_control(d):
+                d = {k: (v.repeat(N // v.shape[0], *([1] * (v.dim() - 1))) if torch.is_tensor(v) and v.shape[0] != N and N % v.shape[0] == 0 else v)
+                     for k, v in d.items()}          # num_samples > 1: one conditioning row per sample
+                return dict(d, control=_z)
+            c = [with_control(ci) for ci in c] if isinstance(c, list) else with_control(c)     # list = local prompts, one per window
+            uc = with_control(uc)
         denoiser = FusedDenoiser(self.denoiser, self.model)
         noised_z = torch.randn_like(_z).to(_z.device)
         _samples = self.sampler(denoiser, noised_z, cond=c, uc=uc, x_center=z_stage1, control_scale=control_scale,

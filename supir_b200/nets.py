@@ -45,6 +45,7 @@ class Ctx:
         self.B = B
         self.emb_all = None        # fp32 [B, sum(Cout of all ResBlocks)]
         self.ctx_kv = None         # bf16 [B*Lctx, sum(2*inner)] context K|V projections of every cross-attention
+        self.kv_owned = True       # False: ctx_kv belongs to the caller (projected outside the per-step graph)
         self.Lctx = 0
         self.control_scale = None  # fp32 device scalar
 
@@ -526,8 +527,15 @@ class _UNetBase(nn.Module):
         self._packed_device = self._emb_w.device
         return self
 
-    def _prepare_ctx(self, ctx, t_f32, context_bf16, B, Lctx, y_f32):
-        """K8: timestep + label embedding MLPs and every ResBlock's emb projection; text K|V for all cross-attentions."""
+    def project_context(self, context_bf16, out):
+        """Text K|V of EVERY cross-attention of this network as one GEMM: out[B*Lctx, sum 2*inner] (attention.py:248-251).
+        The context is constant over the sampler steps, so ControlWrapper runs this outside the per-step CUDA graph and
+        only when the context changes."""
+        return ops.gemm(context_bf16, self._ctx_w, out)
+
+    def _prepare_ctx(self, ctx, t_f32, context_bf16, B, Lctx, y_f32, ctx_kv=None):
+        """K8: timestep + label embedding MLPs and every ResBlock's emb projection; text K|V for all cross-attentions
+        (`ctx_kv`: already projected by project_context)."""
         p = ctx.pool
         temb = p.get((B, self.model_channels), torch.float32)
         ops.timestep_embedding(t_f32, temb)
@@ -541,12 +549,14 @@ class _UNetBase(nn.Module):
         ctx.emb_all = p.get((B, self._emb_w.shape[0]), torch.float32)
         ops.linear_small_m(emb, self._emb_w, self._emb_b, ctx.emb_all)
         p.put(temb, h1, e_t, h2, emb)
-        ctx.ctx_kv = p.get((B * Lctx, self._ctx_kv_cols))
-        ops.gemm(context_bf16, self._ctx_w, ctx.ctx_kv)
+        ctx.kv_owned = ctx_kv is None
+        if ctx_kv is None:
+            ctx_kv = self.project_context(context_bf16, p.get((B * Lctx, self._ctx_kv_cols)))
+        ctx.ctx_kv = ctx_kv
         ctx.Lctx = Lctx
 
     def _release_ctx(self, ctx):
-        ctx.pool.put(ctx.emb_all, ctx.ctx_kv)
+        ctx.pool.put(ctx.emb_all, ctx.ctx_kv if ctx.kv_owned else None)
         ctx.emb_all = ctx.ctx_kv = None
 
 
@@ -563,10 +573,10 @@ class GLVControl(_UNetBase):
                            num_head_channels, transformer_depth, context_dim, adm_in_channels, num_classes, kw)
         self.input_hint_block = TimestepEmbedSequential(ConvIn(in_channels, model_channels, 3, padding=1))
 
-    def run(self, ctx, control_x, t_f32, xt, context_bf16, Lctx, y_f32):
+    def run(self, ctx, control_x, t_f32, xt, context_bf16, Lctx, y_f32, ctx_kv=None):
         """control_x, xt: fp32 NCHW. Returns list[Act] (the reference's `hs`)."""
         B = xt.shape[0]
-        self._prepare_ctx(ctx, t_f32, context_bf16, B, Lctx, y_f32)
+        self._prepare_ctx(ctx, t_f32, context_bf16, B, Lctx, y_f32, ctx_kv)
         hint = self.input_hint_block[0].run_nchw(ctx, control_x)
         h = self.input_blocks[0][0].run_nchw(ctx, xt, residual=hint)   # conv_in(xt) + guided_hint
         ctx.free(hint)
@@ -625,10 +635,10 @@ class LightGLVUNet(_UNetBase):
         self._out_packed = ops.pack_small_cout_weight(w, self.out[2].bias)
         return self
 
-    def run(self, ctx, x, t_f32, context_bf16, Lctx, y_f32, control, out_nchw):
+    def run(self, ctx, x, t_f32, context_bf16, Lctx, y_f32, control, out_nchw, ctx_kv=None):
         """x fp32 NCHW; control: list[Act] from GLVControl.run; out_nchw: fp32 [B, out_channels, H, W]."""
         B = x.shape[0]
-        self._prepare_ctx(ctx, t_f32, context_bf16, B, Lctx, y_f32)
+        self._prepare_ctx(ctx, t_f32, context_bf16, B, Lctx, y_f32, ctx_kv)
         h = self.input_blocks[0][0].run_nchw(ctx, x)
         hs = [h]
         for blk in list(self.input_blocks)[1:]:

@@ -18,6 +18,9 @@ import torch
 from . import ops
 from .config import instantiate_from_config
 
+import itertools
+
+_RUN_IDS = itertools.count(1)      # names a sampler run (its conditioning is constant) for ControlWrapper's text K|V reuse
 SIGMA_MAX = 14.6146
 f32 = np.float32
 DEFAULT_GUIDER = {"target": "sgm.modules.diffusionmodules.guiders.IdentityGuider"}
@@ -56,6 +59,16 @@ def shard_windows(num_windows, world_size, rank):
     return per, lo, hi
 
 
+def shard_units(num_units, world_size, rank):
+    """Balanced contiguous partition of the (CFG branch, window) units of a tiled step: sizes differ by at most one
+    (98 units over 8 ranks -> 13, 13, 12 x 6 instead of the 14 / 0 a per-window split leaves). Returns (slot size of the
+    padded exchange buffer, first unit, one past the last unit)."""
+    base, rem = divmod(num_units, world_size)
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return base + (1 if rem else 0), lo, hi
+
+
 def balanced_groups(n, max_group):
     """Split n windows into ceil(n / max_group) contiguous groups whose sizes differ by at most one (at most two
     distinct network batch sizes -> at most two captured CUDA graphs)."""
@@ -71,13 +84,22 @@ def balanced_groups(n, max_group):
     return out
 
 
-def exchange_window_outputs(tiles_out, rank, per):
-    """The one collective of a tiled step: in-place all-gather of the per-rank blocks of `tiles_out`
+def exchange_window_outputs(tiles_out, rank, per, group=None):
+    """The one collective of a tiled step on the generic path: in-place all-gather of the per-rank blocks of `tiles_out`
     ([world*per, ...] fp32, rank r owns slots [r*per, (r+1)*per)). NCCL on GPUs, gloo in the CPU tests."""
     import torch.distributed as dist
     mine = tiles_out[rank * per:(rank + 1) * per].reshape(-1).clone()
-    dist.all_gather_into_tensor(tiles_out.view(-1), mine)
+    dist.all_gather_into_tensor(tiles_out.view(-1), mine, group=group)
     return tiles_out
+
+
+def exchange_unit_outputs(padded, rank, per, group=None):
+    """The one collective of a tiled step on the fused path: in-place all-gather of the per-rank slots of `padded`
+    ([world*per, ...] fp32, rank r's units in slots [r*per, r*per + n_r))."""
+    import torch.distributed as dist
+    mine = padded[rank * per:(rank + 1) * per].reshape(-1).clone()
+    dist.all_gather_into_tensor(padded.view(-1), mine, group=group)
+    return padded
 
 
 class FusedDenoiser:
@@ -145,7 +167,7 @@ class RestoreEDMSampler(BaseDiffusionSampler):
             ops.edm_pre(x, eps if k["gamma"] > 0 else None, k["noise_mul"], c_in, x_hat, net_in)
             cpair = {key: torch.cat((uc[key], cond[key]), 0) for key in ("vector", "crossattn", "control")}
             t = torch.full((2 * N,), idx, dtype=torch.long, device=x.device)
-            net_out = denoiser.network(net_in, t, cpair, k["control_scale"])
+            net_out = denoiser.network(net_in, t, cpair, k["control_scale"], context_token=k.get("context_token"))
             x_next = torch.empty_like(x)
             ops.edm_post(x_hat, net_out, x_center if k["use_restore"] else None, -sq, self.guider.scale_host(k["sigma_hat"]),
                          k["restore_mul"], k["sigma_hat"], k["dt"], x_next)
@@ -175,14 +197,35 @@ class RestoreEDMSampler(BaseDiffusionSampler):
     @torch.no_grad()
     def __call__(self, denoiser, x, cond, uc=None, num_steps=None, x_center=None, control_scale=1.0,
                  use_linear_control_scale=False, control_scale_start=0.0):
-        uc = cond if uc is None else uc
-        x, sigmas = self.prepare_sampling_loop(x, num_steps)
-        xc = None if x_center is None else x_center.contiguous().float()
-        for i in range(len(sigmas) - 1):
-            k = self.step_constants(sigmas, i, control_scale, use_linear_control_scale, control_scale_start)
-            eps = torch.randn_like(x) if k["gamma"] > 0 else None
-            x = self._step(denoiser, x, eps, cond, uc, xc, k)
-        return x
+        run = self.begin(denoiser, x, cond, uc, num_steps, x_center, control_scale, use_linear_control_scale, control_scale_start)
+        for i in range(run.num_steps):
+            run.step(i)
+        return run.x
+
+    @torch.no_grad()
+    def begin(self, denoiser, x, cond, uc=None, num_steps=None, x_center=None, control_scale=1.0,
+              use_linear_control_scale=False, control_scale_start=0.0):
+        """Set up a run and return an object whose .step(i) advances one EDM step (bench.py times those)."""
+        return _EDMRun(self, denoiser, x, cond, cond if uc is None else uc, num_steps, x_center, control_scale,
+                       use_linear_control_scale, control_scale_start)
+
+
+class _EDMRun:
+    def __init__(self, smp, denoiser, x, cond, uc, num_steps, x_center, control_scale, lin_cs, cs_start):
+        self.smp, self.denoiser, self.cond, self.uc = smp, denoiser, cond, uc
+        self.uid = next(_RUN_IDS)
+        self.control_scale, self.lin_cs, self.cs_start = control_scale, lin_cs, cs_start
+        self.x, self.sigmas = smp.prepare_sampling_loop(x, num_steps)
+        self.xc = None if x_center is None else x_center.contiguous().float()
+        self.num_steps = len(self.sigmas) - 1
+
+    @torch.no_grad()
+    def step(self, i):
+        k = self.smp.step_constants(self.sigmas, i, self.control_scale, self.lin_cs, self.cs_start)
+        k["context_token"] = self.uid          # cond / uc are this run's, unchanged over its steps
+        eps = torch.randn_like(self.x) if k["gamma"] > 0 else None
+        self.x = self.smp._step(self.denoiser, self.x, eps, self.cond, self.uc, self.xc, k)
+        return self.x
 
 
 class TiledRestoreEDMSampler(RestoreEDMSampler):
@@ -190,7 +233,11 @@ class TiledRestoreEDMSampler(RestoreEDMSampler):
         super().__init__(*args, **kwargs)
         self.tile_size, self.tile_stride = tile_size, tile_stride
         self.tile_batch = max(1, int(tile_batch))        # windows stacked into one network call
-        self.shard = True                                # shard windows over torch.distributed ranks when initialised
+        # Sharding the windows of ONE image over torch.distributed ranks is opt-in (a data-parallel caller with a different
+        # image per rank must not meet collectives): set `.shard = True` (and optionally `.process_group`) on every rank,
+        # with identical inputs and RNG state on all of them (SUPIRModel.enable_tile_sharding does this).
+        self.shard = False
+        self.process_group = None
         self._weights = None
 
     @property
@@ -217,16 +264,29 @@ class TiledRestoreEDMSampler(RestoreEDMSampler):
 
 
 class _TiledRun:
+    """One tiled sampling run (sampling.py:600-660). Two execution paths:
+
+    fused (this package's FusedDenoiser + a guider with a host-side scale): the step arithmetic of ALL windows is two
+      kernels (edm_pre / edm_post) around the network calls, and the work items handed to the network are the 2 x windows
+      (CFG branch, window) UNITS in branch-major order (all unconditional rows, then all conditional rows — the layout
+      edm_post reduces). Under sharding a rank runs a balanced contiguous range of units (they need not be pairs: both
+      branches of a window see the same input), ONE all-gather moves the raw network outputs, and every rank finishes the
+      step (edm_post + ordered Gaussian blend) on all windows -> bit-identical x on every rank and identical to the
+      single-GPU run, because every kernel treats batch rows independently.
+    generic (any callable denoiser, e.g. the reference's own lambda): windows are sharded as CFG pairs and the per-window
+      step results are exchanged (the round-1 path)."""
+
     def __init__(self, smp, denoiser, x, cond, uc, num_steps, x_center, control_scale, use_linear_control_scale,
                  control_scale_start):
         import torch.distributed as dist
         self.smp, self.denoiser, self.cond = smp, denoiser, cond
+        self.uid = next(_RUN_IDS)
         self.control_scale, self.lin_cs, self.cs_start = control_scale, use_linear_control_scale, control_scale_start
         self.use_local_prompt = isinstance(cond, list)
         b, ch, h, w = x.shape
         T = smp.tile_size
         windows = _sliding_windows(h, w, T, smp.tile_stride)
-        nw = len(windows)
+        nw = self.nw = len(windows)
         if self.use_local_prompt:
             assert len(cond) == nw, "Number of local prompts should be equal to number of tiles"
             lq = cond[0]["control"]
@@ -235,36 +295,107 @@ class _TiledRun:
         self.uc = (cond[0] if self.use_local_prompt else cond) if uc is None else uc
         lq = lq.contiguous().float()
         xc = x_center.contiguous().float()
-        self.world, self.rank = ((dist.get_world_size(), dist.get_rank())
+        self.group = smp.process_group
+        self.world, self.rank = ((dist.get_world_size(self.group), dist.get_rank(self.group))
                                  if smp.shard and dist.is_available() and dist.is_initialized() else (1, 0))
-        self.per, self.lo, self.hi = shard_windows(nw, self.world, self.rank)
-        slots = self.per * self.world
-        table = torch.full((slots, 4), -1, dtype=torch.int32)
-        table[:nw] = torch.tensor(windows, dtype=torch.int32)
-        self.table_dev = table.to(x.device)
-        self.my_table = self.table_dev[self.lo:self.hi].contiguous()
+        self.fused = isinstance(denoiser, FusedDenoiser) and hasattr(smp.guider, "scale_host")
         self.weights64 = smp.tile_weights[0, 0].contiguous()
         self.x, self.sigmas = smp.prepare_sampling_loop(x, num_steps)
         self.num_steps = len(self.sigmas) - 1
         self.shape = (b, ch, T)
-        self.tiles_out = torch.zeros((slots, b, ch, T, T), dtype=torch.float32, device=x.device)
-        self.n_mine = self.hi - self.lo
-        if self.n_mine > 0:     # per-window conditioning is constant across steps: gather it once
-            self.lq_t = torch.empty((self.n_mine, b, ch, T, T), dtype=torch.float32, device=x.device)
+        dev = x.device
+        if self.fused:
+            self.table_dev = torch.tensor(windows, dtype=torch.int32).to(dev)
+            self.per, self.lo, self.hi = shard_units(2 * nw, self.world, self.rank)
+            self.n_mine = self.hi - self.lo
+            # per-window conditioning is constant across steps: gather it once (all windows: every rank finishes the step)
+            self.lq_t = torch.empty((nw, b, ch, T, T), dtype=torch.float32, device=dev)
             self.xc_t = torch.empty_like(self.lq_t)
-            ops.tile_gather(lq, self.my_table, T, self.lq_t)
-            ops.tile_gather(xc, self.my_table, T, self.xc_t)
+            ops.tile_gather(lq, self.table_dev, T, self.lq_t)
+            ops.tile_gather(xc, self.table_dev, T, self.xc_t)
+            # conditioning rows of this rank's units (unit u: branch u // nw (0 = unconditional), window u % nw)
+            def unit_cond(u, key):
+                if u < nw:
+                    return self.uc[key]
+                return (cond[u - nw] if self.use_local_prompt else cond)[key]
+            if self.n_mine > 0:
+                units = range(self.lo, self.hi)
+                self.u_ctx = torch.cat([unit_cond(u, "crossattn") for u in units], 0).contiguous()
+                self.u_vec = torch.cat([unit_cond(u, "vector") for u in units], 0).contiguous()
+                self.u_lq = torch.cat([self.lq_t[u % nw] for u in units], 0).contiguous()
+            # network outputs of every unit; padded to equal slots per rank only when the split is uneven
+            self.sizes = [shard_units(2 * nw, self.world, r) for r in range(self.world)]
+            self.even = all(hi - lo == self.per for _, lo, hi in self.sizes)
+            self.units_pad = torch.zeros((self.per * self.world, b, ch, T, T), dtype=torch.float32, device=dev)
+            self.units_all = self.units_pad if self.even else torch.zeros((2 * nw, b, ch, T, T), dtype=torch.float32, device=dev)
+            self.tiles_out = torch.empty((nw, b, ch, T, T), dtype=torch.float32, device=dev)
+        else:
+            self.per, self.lo, self.hi = shard_windows(nw, self.world, self.rank)
+            slots = self.per * self.world
+            table = torch.full((slots, 4), -1, dtype=torch.int32)
+            table[:nw] = torch.tensor(windows, dtype=torch.int32)
+            self.table_dev = table.to(dev)
+            self.my_table = self.table_dev[self.lo:self.hi].contiguous()
+            self.tiles_out = torch.zeros((slots, b, ch, T, T), dtype=torch.float32, device=dev)
+            self.n_mine = self.hi - self.lo
+            if self.n_mine > 0:
+                self.lq_t = torch.empty((self.n_mine, b, ch, T, T), dtype=torch.float32, device=dev)
+                self.xc_t = torch.empty_like(self.lq_t)
+                ops.tile_gather(lq, self.my_table, T, self.lq_t)
+                ops.tile_gather(xc, self.my_table, T, self.xc_t)
 
     @torch.no_grad()
     def step(self, i, eps_noise=None):
-        import torch.distributed as dist
+        smp, x = self.smp, self.x
+        k = smp.step_constants(self.sigmas, i, self.control_scale, self.lin_cs, self.cs_start)
+        if eps_noise is None:
+            eps_noise = torch.randn_like(x)     # drawn every step, on every rank, like the reference (sampling.py:631)
+        x_next = self._step_fused(k, eps_noise) if self.fused else self._step_generic(k, eps_noise)
+        self.x = x_next
+        return x_next
+
+    def _step_fused(self, k, eps_noise):
+        smp, x = self.smp, self.x
+        b, ch, T = self.shape
+        nw, n_mine = self.nw, self.n_mine
+        den = self.denoiser.denoiser
+        sq, idx = den.quantize_host(k["sigma_hat"])
+        c_in = float(f32(1.0) / np.sqrt(f32(sq) * f32(sq) + f32(1.0)))
+        x_t = torch.empty((nw, b, ch, T, T), dtype=torch.float32, device=x.device)
+        ops.tile_gather(x, self.table_dev, T, x_t)
+        e_t = None
+        if k["gamma"] > 0:
+            e_t = torch.empty_like(x_t)
+            ops.tile_gather(eps_noise, self.table_dev, T, e_t)
+        x_hat = torch.empty_like(x_t)
+        net_in = torch.empty((2 * nw, b, ch, T, T), dtype=torch.float32, device=x.device)     # unit u <-> block u (both halves equal)
+        ops.edm_pre(x_t, e_t, k["noise_mul"], c_in, x_hat, net_in)
+        if n_mine > 0:
+            slot0 = self.rank * self.per
+            for g0, g1 in balanced_groups(n_mine, 2 * smp.tile_batch):
+                g = g1 - g0
+                cg = {"control": self.u_lq[g0 * b:g1 * b], "crossattn": self.u_ctx[g0 * b:g1 * b], "vector": self.u_vec[g0 * b:g1 * b]}
+                t = torch.full((g * b,), idx, dtype=torch.long, device=x.device)
+                out = self.denoiser.network(net_in[self.lo + g0:self.lo + g1].reshape(g * b, ch, T, T), t, cg, k["control_scale"],
+                                            context_token=(self.uid, g0))   # the conditioning is constant over this run's steps
+                self.units_pad[slot0 + g0:slot0 + g1] = out.view(g, b, ch, T, T)
+        if self.world > 1:
+            # the ONE exchange of a step: every rank receives the raw network outputs of all units (NCCL all-gather over NVLink)
+            exchange_unit_outputs(self.units_pad, self.rank, self.per, self.group)
+            if not self.even:
+                for r, (_, lo, hi) in enumerate(self.sizes):
+                    self.units_all[lo:hi].copy_(self.units_pad[r * self.per:r * self.per + (hi - lo)])
+        ops.edm_post(x_hat, self.units_all, self.xc_t if k["use_restore"] else None, -sq, smp.guider.scale_host(k["sigma_hat"]),
+                     k["restore_mul"], k["sigma_hat"], k["dt"], self.tiles_out)
+        x_next = torch.empty_like(x)
+        ops.tile_blend(self.tiles_out, self.table_dev, T, self.weights64, x_next)
+        return x_next
+
+    def _step_generic(self, k, eps_noise):
         smp, x = self.smp, self.x
         b, ch, T = self.shape
         n_mine, lo = self.n_mine, self.lo
         cond, uc = self.cond, self.uc
-        k = smp.step_constants(self.sigmas, i, self.control_scale, self.lin_cs, self.cs_start)
-        if eps_noise is None:
-            eps_noise = torch.randn_like(x)     # drawn every step, on every rank, like the reference (sampling.py:631)
         if n_mine > 0:
             x_t = torch.empty((n_mine, b, ch, T, T), dtype=torch.float32, device=x.device)
             ops.tile_gather(x, self.my_table, T, x_t)
@@ -286,11 +417,9 @@ class _TiledRun:
                                 self.xc_t[g0:g1].reshape(g * b, ch, T, T), k)
                 self.tiles_out[lo + g0:lo + g1] = out.view(g, b, ch, T, T)
         if self.world > 1:
-            # the ONE exchange of a step: every rank receives all window outputs (NCCL all-gather over NVLink)
-            exchange_window_outputs(self.tiles_out, self.rank, self.per)
+            exchange_window_outputs(self.tiles_out, self.rank, self.per, self.group)
         x_next = torch.empty_like(x)
         ops.tile_blend(self.tiles_out, self.table_dev, T, self.weights64, x_next)
-        self.x = x_next
         return x_next
 
 
@@ -379,20 +508,38 @@ class RestoreDPMPP2MSampler(BaseDiffusionSampler):
         sig = self.host_sigmas(num_steps)
         x0 = torch.empty_like(x, dtype=torch.float32)
         ops.axpby_f32(x.contiguous().float(), float(np.sqrt(f32(1.0) + sig[0] * sig[0])), None, 0.0, x0)
-        n = self.num_steps if num_steps is None else num_steps
-        return x0, get_sigmas_karras(n, sig[-2], sig[0]).numpy().astype(np.float32), len(sig)
+        # the reference asks k-diffusion for self.num_steps sigmas whatever `num_steps` overrides (sampling.py:474-476)
+        return x0, get_sigmas_karras(self.num_steps, sig[-2], sig[0]).numpy().astype(np.float32), len(sig)
 
     @torch.no_grad()
     def __call__(self, denoiser, x, cond, uc=None, num_steps=None, control_scale=1.0, **kwargs):
-        uc = cond if uc is None else uc
-        x, sigmas, num_sigmas = self._schedule(x, num_steps)
-        noise = self.noise_sampler_cls(x, sigmas[-2], sigmas[0])
-        old = None
-        for i in range(num_sigmas - 1):
-            eps = noise(sigmas[i], sigmas[i + 1]) if (i > 0 and sigmas[i + 1] > 1e-14) else None
-            x, old = self.sampler_step(denoiser, old, None if i == 0 else float(sigmas[i - 1]), float(sigmas[i]),
-                                       float(sigmas[i + 1]), x, cond, uc, eps, control_scale)
-        return x
+        run = self.begin(denoiser, x, cond, uc, num_steps, control_scale=control_scale)
+        for i in range(run.num_steps):
+            run.step(i)
+        return run.x
+
+    @torch.no_grad()
+    def begin(self, denoiser, x, cond, uc=None, num_steps=None, control_scale=1.0, **kwargs):
+        return _DPMRun(self, denoiser, x, cond, cond if uc is None else uc, num_steps, control_scale)
+
+
+class _DPMRun:
+    def __init__(self, smp, denoiser, x, cond, uc, num_steps, control_scale):
+        self.smp, self.denoiser, self.cond, self.uc, self.control_scale = smp, denoiser, cond, uc, control_scale
+        self.x, self.sigmas, num_sigmas = smp._schedule(x, num_steps)
+        self.noise = smp.noise_sampler_cls(self.x, self.sigmas[-2], self.sigmas[0])
+        self.old = None
+        self.num_steps = num_sigmas - 1
+
+    @torch.no_grad()
+    def step(self, i):
+        sig = self.sigmas
+        eps = self.noise(sig[i], sig[i + 1]) if (i > 0 and sig[i + 1] > 1e-14) else None
+        if i == 0:
+            self.old = None
+        self.x, self.old = self.smp.sampler_step(self.denoiser, self.old, None if i == 0 else float(sig[i - 1]), float(sig[i]),
+                                                 float(sig[i + 1]), self.x, self.cond, self.uc, eps, self.control_scale)
+        return self.x
 
 
 class TiledRestoreDPMPP2MSampler(RestoreDPMPP2MSampler):

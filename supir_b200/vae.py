@@ -9,8 +9,8 @@ Parameters carry the reference's names; compute is the C-ABI kernels. The networ
 the same steps with ALL tiles resident in HBM (the reference parks them on the CPU between GroupNorm layers); at each
 GroupNorm the per-tile (mean, biased var) are merged with the reference's pixel-weighted rule (tilevae.py:629-648) by a
 kernel and applied to every tile. Tile bboxes / crops are integer host code, bit-identical to the reference.
-Under torch.distributed the tiles are sharded over ranks: per GroupNorm layer one all-gather of per-tile statistics
-(a few KB), and one all-gather of the cropped output tiles at the end.
+Opt-in (`VAEHook.shard = True`) the tiles are sharded over torch.distributed ranks: per GroupNorm layer one all-gather of
+per-tile statistics (a few KB), and one all-gather of the cropped output tiles at the end.
 """
 import math
 
@@ -308,8 +308,13 @@ class _VAENet(nn.Module):
     forward = original_forward
 
     @torch.no_grad()
-    def tiled_forward(self, z, tile_size):
-        """VAEHook.vae_tile_forward with fast_mode=False (tilevae.py:819-970), tiles resident in HBM, optional rank sharding."""
+    def tiled_forward(self, z, tile_size, shard=False, group=None):
+        """VAEHook.vae_tile_forward with fast_mode=False (tilevae.py:819-970), tiles resident in HBM.
+
+        `shard=True` (opt-in; torch.distributed initialised, identical input on every rank) deals the tiles round-robin over
+        the ranks of `group`. Exchanges: per GroupNorm layer ONE all-gather of the per-tile (mean, var) rows (a few KB),
+        and at the end ONE all-gather of the cropped output tiles (each rank contributes its crops, packed back to back:
+        the canvas crosses NVLink once, nothing is zero-filled or summed)."""
         import torch.distributed as dist
         self._check(z)
         z = z.float().contiguous()
@@ -317,8 +322,10 @@ class _VAENet(nn.Module):
         dec = self.is_decoder
         in_bboxes, out_bboxes = split_tiles(height, width, tile_size, dec)
         T = len(in_bboxes)
-        world, rank = (dist.get_world_size(), dist.get_rank()) if dist.is_available() and dist.is_initialized() else (1, 0)
-        mine = [i for i in range(T) if i % world == rank] if world > 1 else list(range(T))
+        world, rank = ((dist.get_world_size(group), dist.get_rank(group))
+                       if shard and dist.is_available() and dist.is_initialized() else (1, 0))
+        mine = [i for i in range(T) if i % world == rank]
+        per = (T + world - 1) // world                 # tile i lives in slot i // world of rank i % world
         pool = self._scratch()
         dev = z.device
         self._one = torch.ones(1, dtype=torch.float32, device=dev)
@@ -337,19 +344,19 @@ class _VAENet(nn.Module):
             # cross-tile GroupNorm: per-tile (mean, biased var) -> pixel-weighted merge -> shared apply
             C = step[3]
             n = N * 32
-            t_mean = torch.zeros((T, n), dtype=torch.float32, device=dev)
-            t_var = torch.zeros((T, n), dtype=torch.float32, device=dev)
+            stats = torch.zeros((per, 2, n), dtype=torch.float32, device=dev)      # this rank's tiles, slot-major
             pixels = torch.tensor([float(h * w) for h, w in dims], dtype=torch.float32)
             for i in mine:
                 a = tiles[i]["h"]
                 ws = pool.get((ops.groupnorm_ws_size(a.B, a.HW, a.C),), torch.float64)
                 ops.groupnorm_stats(a.t, a.B, a.HW, ws)
-                ops.groupnorm_finalize(ws, n, a.HW * (C // 32), t_mean[i], t_var[i])
+                ops.groupnorm_finalize(ws, n, a.HW * (C // 32), stats[i // world, 0], stats[i // world, 1])
                 pool.put(ws)
             if world > 1:
-                stats = torch.stack([t_mean, t_var], 0)
-                dist.all_reduce(stats)            # disjoint rows per rank: a sum is an all-gather of the per-tile statistics
-                t_mean, t_var = stats[0].contiguous(), stats[1].contiguous()
+                allst = torch.empty((world, per, 2, n), dtype=torch.float32, device=dev)
+                dist.all_gather_into_tensor(allst.view(-1), stats.view(-1), group=group)
+                stats = allst.transpose(0, 1).reshape(per * world, 2, n)            # row slot * world + rank == tile index
+            t_mean, t_var = stats[:T, 0].contiguous(), stats[:T, 1].contiguous()
             wts = pixels / pixels.max()
             wts = (wts / wts.sum()).to(dev)      # GroupNormParam.summary (tilevae.py:629-648)
             mean = torch.empty(n, dtype=torch.float32, device=dev)
@@ -359,14 +366,33 @@ class _VAENet(nn.Module):
                 tiles[i]["fuse_silu"] = fuse
                 self._norm_apply(pool, step, tiles[i], mean=mean, var=var)
         s_out = (height * 8, width * 8) if dec else (height // 8, width // 8)
-        result = torch.zeros((N, self._conv_out[2]) + s_out, dtype=torch.float32, device=dev)
+        Cout = self._conv_out[2]
+        result = torch.empty((N, Cout) + s_out, dtype=torch.float32, device=dev)
+        # crop geometry of every tile from the tracked tile sizes (host integers, identical on all ranks)
+        crops = [crop_margins(dims[i][0], dims[i][1], in_bboxes[i], out_bboxes[i], dec) for i in range(T)]
+        if world == 1:
+            for i in mine:
+                ob = out_bboxes[i]
+                y0, y1, x0, x1 = crops[i]
+                self._finish_tile(pool, tiles[i], result[:, :, ob[2]:ob[3], ob[0]:ob[1]], crop=(y0, x0, y1 - y0, x1 - x0))
+            return result
+        # sharded: every rank packs its cropped tiles back to back; one all-gather; paste
+        numel = [N * Cout * (c[1] - c[0]) * (c[3] - c[2]) for c in crops]
+        offs, fill = {}, [0] * world
+        for i in range(T):
+            offs[i] = fill[i % world]
+            fill[i % world] += numel[i]
+        slot = max(fill)
+        packed = torch.empty((world, slot), dtype=torch.float32, device=dev)
         for i in mine:
-            a = tiles[i]["h"]
+            y0, y1, x0, x1 = crops[i]
+            view = packed[rank, offs[i]:offs[i] + numel[i]].view(N, Cout, y1 - y0, x1 - x0)
+            self._finish_tile(pool, tiles[i], view, crop=(y0, x0, y1 - y0, x1 - x0))
+        dist.all_gather_into_tensor(packed.view(-1), packed[rank].clone(), group=group)
+        for i in range(T):
+            y0, y1, x0, x1 = crops[i]
             ob = out_bboxes[i]
-            y0, y1, x0, x1 = crop_margins(a.H, a.W, in_bboxes[i], ob, dec)
-            self._finish_tile(pool, tiles[i], result[:, :, ob[2]:ob[3], ob[0]:ob[1]], crop=(y0, x0, y1 - y0, x1 - x0))
-        if world > 1:
-            dist.all_reduce(result)               # output tiles are disjoint: sum == gather
+            result[:, :, ob[2]:ob[3], ob[0]:ob[1]].copy_(packed[i % world, offs[i]:offs[i] + numel[i]].view(N, Cout, y1 - y0, x1 - x0))
         return result
 
 
@@ -483,12 +509,13 @@ class VAEHook:
             raise NotImplementedError("fast-mode tiled VAE is disabled by SUPIR (SUPIR_model.py:142-150) and not implemented")
         self.net, self.tile_size, self.is_decoder = net, tile_size, is_decoder
         self.pad = 11 if is_decoder else 32
+        self.shard, self.process_group = False, None      # tile sharding over torch.distributed ranks is opt-in
 
     def __call__(self, x):
         B, C, H, W = x.shape
         if max(H, W) <= self.pad * 2 + self.tile_size:
             return self.net.original_forward(x)
-        return self.net.tiled_forward(x, self.tile_size)
+        return self.net.tiled_forward(x, self.tile_size, shard=self.shard, group=self.process_group)
 
     def split_tiles(self, h, w):
         return split_tiles(h, w, self.tile_size, self.is_decoder)

@@ -31,18 +31,28 @@ class _Plan:
         self.y = torch.zeros(B, y_dim, **f32)
         self.cs = torch.ones(1, **f32)
         self.out = torch.zeros(B, wrapper.diffusion_model.out_channels, H, W, **f32)
+        # text K|V projections of both networks: computed OUTSIDE the captured graph, only when the context changes
+        # (it is constant over the sampler steps; attention.py:248-251 recomputes it in every call)
+        self.kv_ctrl = torch.zeros(B * Lctx, wrapper.control_model._ctx_kv_cols, dtype=torch.bfloat16, device=device)
+        self.kv_unet = torch.zeros(B * Lctx, wrapper.diffusion_model._ctx_kv_cols, dtype=torch.bfloat16, device=device)
+        self.context_token = None
         self.pool = ops.Pool()
         self.graph = None
         self.B, self.Lctx = B, Lctx
         self.wrapper = wrapper
 
+    def project_context(self):
+        w = self.wrapper
+        ops.f32_to_bf16(self.context, self.context_bf16)
+        w.control_model.project_context(self.context_bf16, self.kv_ctrl)
+        w.diffusion_model.project_context(self.context_bf16, self.kv_unet)
+
     def _run(self):
         w = self.wrapper
         ctx = Ctx(self.pool, self.B)
         ctx.control_scale = self.cs
-        ops.f32_to_bf16(self.context, self.context_bf16)
-        control = w.control_model.run(ctx, self.control, self.t, self.x, self.context_bf16, self.Lctx, self.y)
-        w.diffusion_model.run(ctx, self.x, self.t, self.context_bf16, self.Lctx, self.y, control, self.out)
+        control = w.control_model.run(ctx, self.control, self.t, self.x, self.context_bf16, self.Lctx, self.y, ctx_kv=self.kv_ctrl)
+        w.diffusion_model.run(ctx, self.x, self.t, self.context_bf16, self.Lctx, self.y, control, self.out, ctx_kv=self.kv_unet)
 
     def build(self):
         self._run()                      # eager warm-up: one-time attribute setup, fills the scratch pool
@@ -70,7 +80,8 @@ class ControlWrapper(nn.Module):
         self.diffusion_model = diffusion_model
         self.control_model = None
         self.dtype = dtype
-        self._plans = {}
+        self._plans = {}                # (B, H, W, Lctx) -> _Plan, most recently used last
+        self.max_plans = int(os.environ.get("SUPIR_B200_MAX_PLANS", "4"))   # each plan owns a captured graph + its activation pool
         self._packed = False
         self._warned = False
         self.replayed_launches = 0      # kernels launched through CUDA-graph replays (supir_launch_count() sees eager ones)
@@ -85,6 +96,10 @@ class ControlWrapper(nn.Module):
         self._plans = {}
         self._packed = False
 
+    def clear_plans(self):
+        """Drop every captured graph and its activation pool (several GB each); the next call re-captures."""
+        self._plans = {}
+
     def _apply(self, fn, *a, **k):
         r = super()._apply(fn, *a, **k)
         self.invalidate()
@@ -97,7 +112,11 @@ class ControlWrapper(nn.Module):
         return self
 
     @torch.no_grad()
-    def forward(self, x: torch.Tensor, t: torch.Tensor, c: dict, control_scale=1, **kwargs) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, t: torch.Tensor, c: dict, control_scale=1, context_token=None, **kwargs) -> torch.Tensor:
+        """`context_token` (any hashable, optional) is the caller's name for the CONTENT of c['crossattn']: while consecutive
+        calls of one input signature carry the same token, the text K|V projections of the previous call are reused (this
+        package's samplers pass a token that is unique per run and batch group — the conditioning is constant over the
+        steps). Without a token they are recomputed on every call, like the reference does."""
         if self.control_model is None:
             raise RuntimeError("ControlWrapper.forward called before load_control_model()")
         if not x.is_cuda:
@@ -115,20 +134,26 @@ class ControlWrapper(nn.Module):
         plan = self._plans.get(key)
         if plan is None:
             plan = _Plan(self, B, H, W, Lctx, context.shape[2], y.shape[1], x.device)
-            self._fill(plan, x, t, context, y, control, control_scale)
+            self._fill(plan, x, t, context, y, control, control_scale, context_token)
             plan.build()
             self._plans[key] = plan
+            while len(self._plans) > max(self.max_plans, 1):      # least recently used first: frees its graph and pool
+                self._plans.pop(next(iter(self._plans)))
         else:
-            self._fill(plan, x, t, context, y, control, control_scale)
+            self._plans[key] = self._plans.pop(key)               # mark as most recently used
+            self._fill(plan, x, t, context, y, control, control_scale, context_token)
         plan.launch()
         return plan.out.clone()
 
     @staticmethod
-    def _fill(plan, x, t, context, y, control, control_scale):
+    def _fill(plan, x, t, context, y, control, control_scale, token=None):
         plan.x.copy_(x)
         plan.control.copy_(control)
         plan.t.copy_(t)
-        plan.context.copy_(context.reshape(plan.context.shape))
+        if token is None or token != plan.context_token:
+            plan.context.copy_(context.reshape(plan.context.shape))
+            plan.project_context()
+            plan.context_token = token
         plan.y.copy_(y)
         if torch.is_tensor(control_scale):
             plan.cs.copy_(control_scale.reshape(-1)[:1])

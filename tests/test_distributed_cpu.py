@@ -54,6 +54,44 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _unit_worker(rank, world, port, q):
+    """Fused path: (CFG branch, window) units in balanced contiguous ranges, padded all-gather, compaction."""
+    import torch.distributed as dist
+    from supir_b200.sampling import exchange_unit_outputs, shard_units
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    nw, N, C, T = 7, 1, 4, 8                      # 14 units over 3 ranks -> 5, 5, 4
+    g = torch.Generator().manual_seed(11)
+    all_units = torch.randn((2 * nw, N, C, T, T), generator=g)
+    per, lo, hi = shard_units(2 * nw, world, rank)
+    pad = torch.zeros((per * world, N, C, T, T))
+    pad[rank * per:rank * per + (hi - lo)] = all_units[lo:hi]
+    exchange_unit_outputs(pad, rank, per)
+    compact = torch.zeros_like(all_units)
+    for r in range(world):
+        _, l, h = shard_units(2 * nw, world, r)
+        compact[l:h] = pad[r * per:r * per + (h - l)]
+    q.put((rank, bool(torch.equal(compact, all_units)), hi - lo))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_units_all_gather_equals_single_process(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_unit_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r[0] for r in res) == list(range(world))
+    assert all(r[1] for r in res), res
+    assert sum(r[2] for r in res) == 14 and max(r[2] for r in res) - min(r[2] for r in res) <= 1
+
+
 @pytest.mark.parametrize("world", [2])
 def test_sharded_windows_all_gather_equals_single_process(world):
     ctx = mp.get_context("spawn")

@@ -88,13 +88,14 @@ def test_gemm_bench_shapes_all_tiles_and_pair_modes(shape):
     ref = _ref_gemm(a, w, bias, res, act)
     lib = native.load()
     try:
-        for pair in (0, 2):
+        for pair, epi in ((0, 0), (2, 0), (2, 1), (0, 1)):
             for bn in (0, 64, 128, 160, 256):
                 lib.supir_set_gemm_pair_mode(pair)
+                lib.supir_set_gemm_epilogue_mode(epi)
                 lib.supir_set_gemm_tile_n(bn)
                 out = torch.full((M, n_out), float("nan"), dtype=BF, device="cuda")
                 ops.gemm(a, w, out, bias=bias, residual=res, act=act)
-                _check(out, ref, f"gemm {shape} tile_n={bn} pair={pair}")
+                _check(out, ref, f"gemm {shape} tile_n={bn} pair={pair} warp_epilogue={epi}")
         # direct-store epilogue (the fallback for fp32 outputs / unaligned shapes) at the same shape
         lib.supir_set_gemm_pair_mode(1)
         lib.supir_set_gemm_tile_n(0)
@@ -108,6 +109,7 @@ def test_gemm_bench_shapes_all_tiles_and_pair_modes(shape):
             _check(out32, ref, f"gemm {shape} fp32 out")
     finally:
         lib.supir_debug_force_direct_epilogue(0)
+        lib.supir_set_gemm_epilogue_mode(-1)
         lib.supir_set_gemm_pair_mode(1)
         lib.supir_set_gemm_tile_n(0)
 
@@ -153,13 +155,15 @@ def test_conv3x3_bench_shapes(shape):
         ref[b0 * H * W:(b0 + nb) * H * W] = y
     lib = native.load()
     try:
-        for pair, bn in ((1, 0), (0, 256), (2, 256), (0, 128), (0, 160), (0, 64)):
+        for pair, bn, epi in ((1, 0, 0), (0, 256, 0), (2, 256, 0), (0, 128, 0), (0, 160, 0), (0, 64, 0), (1, 0, 1), (2, 256, 1), (0, 128, 1)):
             lib.supir_set_gemm_pair_mode(pair)
+            lib.supir_set_gemm_epilogue_mode(epi)
             lib.supir_set_gemm_tile_n(bn)
             out = torch.full((B * H * W, Cout), float("nan"), dtype=BF, device="cuda")
             ops.conv3x3(x, B, H, W, wp, out, bias=bias, rowvec=rv, residual=res, act=act)
-            _check(out, ref, f"conv {shape} tile_n={bn} pair={pair}")
+            _check(out, ref, f"conv {shape} tile_n={bn} pair={pair} warp_epilogue={epi}")
     finally:
+        lib.supir_set_gemm_epilogue_mode(-1)
         lib.supir_set_gemm_pair_mode(1)
         lib.supir_set_gemm_tile_n(0)
 

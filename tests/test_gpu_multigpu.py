@@ -1,0 +1,27 @@
+"""Multi-GPU parity on real devices (skips below 2 GPUs): the unit-sharded tiled sampler and the tile-sharded VAE over NCCL
+give bit-identical results to the single-GPU path on every rank (tools/check_multigpu.py run under torchrun)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_sharded_sampler_and_vae_bit_identical_to_single_gpu():
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 CUDA devices")
+    world = 2 if n < 4 else (3 if n < 8 else 8)          # 3 ranks: 2 x 20 windows... uneven unit split is exercised as well
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tools", "check_multigpu.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+    res = json.loads(line)
+    print(res)
+    assert res["sampler_sharded_equals_single"] and res["identical_on_all_ranks"] and res["vae_sharded_equals_single"]

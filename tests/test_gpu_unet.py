@@ -54,3 +54,29 @@ def test_unet_fullwidth_depth1_vs_reference_and_oracle():
     ref2 = ounet.light_glv_unet_forward(sd, x, t, cond["crossattn"], cond["vector"], control, 0.3, 320, 64, prefix="diffusion_model.")
     out3 = w(x.cuda(), t.cuda(), cc, control_scale=0.3).cpu()
     assert rel_fro(out3, ref2) <= 2e-2
+
+
+def test_context_token_reuses_text_kv_only_for_the_same_token():
+    """ControlWrapper recomputes the text K|V projections unless the caller names the context content with a token."""
+    g = np.load(os.path.join(G, "unet_fullwidth_depth1.npz"))
+    cfg = json.loads(str(g["cfg"]))
+    sd = make_state_dict(json.loads(str(g["shapes"])), seed=31)
+    w = build_wrapper(cfg, sd)
+    x = randn((2, 4, 16, 16), 41).cuda()
+    t = torch.tensor([950, 120]).cuda()
+    c1 = {"control": randn((2, 4, 16, 16), 42).cuda(), "crossattn": randn((2, 77, 2048), 43).cuda(), "vector": randn((2, 2816), 44).cuda()}
+    c2 = dict(c1, crossattn=randn((2, 77, 2048), 99).cuda())
+    base1 = w(x, t, c1, control_scale=0.8)
+    base2 = w(x, t, c2, control_scale=0.8)
+    assert not torch.equal(base1, base2)
+    a = w(x, t, c1, control_scale=0.8, context_token=("run", 1))
+    b = w(x, t, c1, control_scale=0.8, context_token=("run", 1))          # reuse
+    c = w(x, t, c2, control_scale=0.8, context_token=("run", 2))          # new token -> recomputed
+    d = w(x, t, c2, control_scale=0.8)                                     # no token -> recomputed
+    assert torch.equal(a, base1) and torch.equal(b, base1) and torch.equal(c, base2) and torch.equal(d, base2)
+    # plan cache is bounded (least recently used evicted)
+    w.max_plans = 2
+    for side in (8, 16, 24):
+        xs = randn((2, 4, side, side), 5).cuda()
+        w(xs, t, dict(c1, control=xs), control_scale=1.0)
+    assert len(w._plans) == 2 and (2, 8, 8, 77) not in w._plans

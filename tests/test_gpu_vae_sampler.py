@@ -49,6 +49,25 @@ def test_vae_tiny_untiled_and_tiled_vs_reference():
     assert rel_fro(dec, ovae.decode(sd, z.cpu(), scale_factor=1.0)) <= 3e-2
 
 
+def test_vae_repacks_after_a_second_load_state_dict():
+    """gradio_demo*.py switch checkpoints with model.load_state_dict(..., strict=False) at run time (gradio_demo_tiled.py:130,134):
+    the kernel-layout weights must follow."""
+    from supir_b200 import vae
+    g = np.load(os.path.join(G, "vae_tiny.npz"))
+    cfg = json.loads(str(g["cfg"]))
+    shapes = json.loads(str(g["shapes"]))
+    with torch.device("cuda"):
+        ae = vae.AutoencoderKLInferenceWrapper(embed_dim=4, ddconfig=cfg, lossconfig={"target": "torch.nn.Identity"})
+    ae.load_state_dict(make_state_dict(shapes, seed=71), strict=True)
+    z = randn((1, 4, 8, 6), 82).cuda()
+    d1 = ae.decoder(z).clone()
+    ae.load_state_dict(make_state_dict(shapes, seed=72), strict=False)
+    d2 = ae.decoder(z).clone()
+    assert not torch.allclose(d1, d2)
+    ae.load_state_dict(make_state_dict(shapes, seed=71), strict=False)
+    assert torch.equal(ae.decoder(z), d1)
+
+
 def toy_network(x, t, c, control_scale):
     tt = (t.float() / 1000.0).view(-1, 1, 1, 1)
     v = c["vector"].mean(dim=1).view(-1, 1, 1, 1)

@@ -103,7 +103,23 @@ def test_balanced_groups(n, cap):
         assert len(set(sizes)) <= 2             # at most two network batch sizes -> at most two captured graphs
 
 
+@settings(max_examples=300, deadline=None)
+@given(st.integers(0, 600), st.integers(1, 16))
+def test_shard_units_balanced_contiguous(n, world):
+    spans = [sampling.shard_units(n, world, r) for r in range(world)]
+    covered = [u for _, lo, hi in spans for u in range(lo, hi)]
+    assert covered == list(range(n))
+    sizes = [hi - lo for _, lo, hi in spans]
+    assert max(sizes) - min(sizes) <= 1 and all(per == max(sizes) for per, _, _ in spans)
+
+
+def test_98_units_over_8_ranks():
+    """The bench workload's fused-path partition at N = 8: 49 windows x CFG pair = 98 units -> 13, 13, 12 x 6 (no idle rank)."""
+    assert [hi - lo for _, lo, hi in (sampling.shard_units(98, 8, r) for r in range(8))] == [13, 13] + [12] * 6
+    assert [hi - lo for _, lo, hi in (sampling.shard_units(98, 4, r) for r in range(4))] == [25, 25, 24, 24]
+
+
 def test_49_windows_over_8_ranks():
-    """The bench workload's partition at N = 8: seven windows on ranks 0-6, rank 7 idle but still in the exchange."""
+    """The generic (foreign-denoiser) path still shards whole windows: seven on ranks 0-6, rank 7 only in the exchange."""
     spans = [sampling.shard_windows(49, 8, r) for r in range(8)]
     assert [hi - lo for _, lo, hi in spans] == [7] * 7 + [0] and spans[0][0] == 7

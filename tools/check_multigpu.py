@@ -1,5 +1,5 @@
-"""torchrun --nproc-per-node N tools/check_multigpu.py : the window-sharded tiled sampler and the tile-sharded VAE give the
-same result as the single-GPU path (bit-identical latents; VAE equal up to fp32 summation of disjoint tiles = exact)."""
+"""torchrun --nproc-per-node N tools/check_multigpu.py : the unit-sharded tiled sampler and the tile-sharded VAE give the
+same result as the single-GPU path, bit for bit, on every rank (also run by tests/test_gpu_multigpu.py when >= 2 GPUs)."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -16,11 +16,12 @@ def main():
     g = np.load(os.path.join(ROOT, "tests", "golden", "unet_fullwidth_depth1.npz"))
     cfg = json.loads(str(g["cfg"]))
     sd = make_state_dict(json.loads(str(g["shapes"])), seed=31)
-    with torch.device("cuda"):
+    with torch.device("meta"):
         unet = nets.LightGLVUNet(mode="XL-base", project_type="ZeroSFT", project_channel_scale=2, **cfg)
         ctrl = nets.GLVControl(input_upscale=1, **cfg)
     net = wrappers.ControlWrapper(unet, dtype=torch.bfloat16)
     net.load_control_model(ctrl)
+    net.to_empty(device="cuda")
     net.load_state_dict(sd)
     disc = {"target": "sgm.modules.diffusionmodules.discretizer.LegacyDDPMDiscretization"}
     den = dn.DiscreteDenoiserWithControl(weighting_config={"target": "sgm.modules.diffusionmodules.denoiser_weighting.EpsWeighting"},
@@ -49,14 +50,16 @@ def main():
         ae = vae.AutoencoderKLInferenceWrapper(embed_dim=4, ddconfig=json.loads(str(gv["cfg"])), lossconfig={"target": "torch.nn.Identity"})
     ae.load_state_dict(make_state_dict(json.loads(str(gv["shapes"])), seed=71))
     zbig = randn((1, 4, 40, 52), 84).cuda()
-    d_sharded = ae.decoder.tiled_forward(zbig, 16)
+    d_sharded = ae.decoder.tiled_forward(zbig, 16, shard=True)
+    d_single = ae.decoder.tiled_forward(zbig, 16, shard=False)
+    vae_same = torch.equal(d_sharded, d_single)
     ref = torch.from_numpy(gv["dec_tiled"]).cuda()
     rel = float((d_sharded - ref).norm() / ref.norm())
     if rank == 0:
         print(json.dumps({"world": world, "sampler_sharded_equals_single": same, "identical_on_all_ranks": same_ranks,
-                          "vae_sharded_rel_fro_vs_reference": rel, "finite": bool(torch.isfinite(a).all())}))
+                          "vae_sharded_rel_fro_vs_reference": rel, "vae_sharded_equals_single": vae_same, "finite": bool(torch.isfinite(a).all())}))
     dist.barrier()
     dist.destroy_process_group()
-    assert same and same_ranks and rel < 3e-2
+    assert same and same_ranks and vae_same and rel < 3e-2
 
 main()
