@@ -209,6 +209,9 @@ int supir_plane_stats(const float* x, int planes, long long hw, double* ws, long
 /* adaptive_instance_normalization (colorfix.py:45-71): (content - mean_c) / std_c * std_s + mean_s, unbiased var + 1e-5 */
 int supir_adain_apply(const float* content, const double* content_stats, const double* style_stats, float* out, int planes,
                       long long hw, void* stream);
+/* Tensor2PIL (SUPIR/util.py:87-94): bicubic resize of one fp32 [C, H, W] image in [-1, 1] to (h0, w0) exactly as
+ * torch.nn.functional.interpolate(mode='bicubic') computes it, then * 127.5 + 127.5, clip, truncate: out uint8 [h0, w0, C]. */
+int supir_image_to_uint8_bicubic(const float* x, int C, int H, int W, unsigned char* out, int h0, int w0, void* stream);
 
 #ifdef __cplusplus
 }

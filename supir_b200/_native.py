@@ -59,6 +59,7 @@ _SIGS = {
     "supir_wavelet_level": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "supir_plane_stats": [c_void_p, c_int, c_ll, c_void_p, c_ll, c_void_p],
     "supir_adain_apply": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_void_p],
+    "supir_image_to_uint8_bicubic": [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p],
     "supir_gaussian_latent": [c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_ll, c_void_p],
 }
 _SPECIAL = {

@@ -219,7 +219,9 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const uint32_t tmem_base = *tmem_ptr;
 
     if (warp < 4) {
-      // register budgets: <2,*> 384 threads x 168 -> 64 / 224;  <1,*> 256 threads x 128 (two CTAs per SM) -> 56 / 200
+      // register budgets (the CTA's pool is what the launch reserved: 168 regs x 384 threads, or 128 x 256 with two CTAs per
+      // SM): <2,*> 64 control / 216 softmax, <1,*> 56 / 200. What the four control warps give up must cover what the softmax
+      // warps ask for, or the last setmaxnreg.inc waits forever: (168-64)*4 = 416 >= (216-168)*8 = 384; (128-56)*4 = (200-128)*4.
       if (TILES == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
       else asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
       if (warp == 0) {
@@ -320,7 +322,7 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
       }
     } else {
-        if (TILES == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        if (TILES == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
         else asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
         // ---------------- softmax / output warps ----------------
         const int x = (warp - 4) >> 2;                          // tile 0 (A) or 1 (B)

@@ -87,6 +87,46 @@ __global__ void adain_apply_kernel(const float* __restrict__ content, const doub
     }
 }
 
+// Tensor2PIL (SUPIR/util.py:87-94): bicubic resize (torch interpolate, align_corners=False, A = -0.75, border indices clamped),
+// then x * 127.5 + 127.5, clip to [0, 255], truncate to uint8, HWC. Same operation order as ATen's upsample_bicubic2d (rows
+// first, then columns; coefficient polynomials as in aten/src/ATen/native/UpSample.h) so the bytes match torch's.
+__device__ __forceinline__ float cubic_conv1(float x, float A) { return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
+__device__ __forceinline__ float cubic_conv2(float x, float A) { return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
+__device__ __forceinline__ void cubic_coeffs(float t, float (&c)[4]) {
+    const float A = -0.75f;
+    c[0] = cubic_conv2(t + 1.0f, A);
+    c[1] = cubic_conv1(t, A);
+    const float u = 1.0f - t;
+    c[2] = cubic_conv1(u, A);
+    c[3] = cubic_conv2(u + 1.0f, A);
+}
+__global__ void image_to_uint8_bicubic_kernel(const float* __restrict__ x, int C, int H, int W, unsigned char* __restrict__ out,
+                                              int h0, int w0, float scale_h, float scale_w) {
+    const long long total = (long long)h0 * w0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % w0), oy = (int)(i / w0);
+        const float rx = scale_w * (ox + 0.5f) - 0.5f, ry = scale_h * (oy + 0.5f) - 0.5f;
+        const int ix = (int)floorf(rx), iy = (int)floorf(ry);
+        float cx[4], cy[4];
+        cubic_coeffs(rx - ix, cx);
+        cubic_coeffs(ry - iy, cy);
+        for (int c = 0; c < C; ++c) {
+            const float* pl = x + (long long)c * H * W;
+            float rows[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float* r = pl + (long long)min(max(iy - 1 + k, 0), H - 1) * W;
+                rows[k] = r[min(max(ix - 1, 0), W - 1)] * cx[0] + r[min(max(ix, 0), W - 1)] * cx[1] +
+                          r[min(max(ix + 1, 0), W - 1)] * cx[2] + r[min(max(ix + 2, 0), W - 1)] * cx[3];
+            }
+            float v = rows[0] * cy[0] + rows[1] * cy[1] + rows[2] * cy[2] + rows[3] * cy[3];
+            v = v * 127.5f + 127.5f;
+            v = fminf(fmaxf(v, 0.f), 255.f);
+            out[i * C + c] = (unsigned char)v;           // truncation, like numpy's astype(np.uint8) on clipped values
+        }
+    }
+}
+
 static const int kStatBlocks = 64;
 
 }  // namespace supir
@@ -130,6 +170,18 @@ extern "C" int supir_adain_apply(const float* content, const double* content_sta
     if (blocks > cap) blocks = cap;
     adain_apply_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(content, content_stats, style_stats,
                                                                                             out, hw, planes);
+    count_launch();
+    SUPIR_CHECK_CUDA(cudaGetLastError());
+    return SUPIR_OK;
+}
+
+extern "C" int supir_image_to_uint8_bicubic(const float* x, int C, int H, int W, unsigned char* out, int h0, int w0, void* stream) {
+    SUPIR_REQUIRE(x && out && C > 0 && H > 0 && W > 0 && h0 > 0 && w0 > 0, "supir_image_to_uint8_bicubic: bad args");
+    const long long total = (long long)h0 * w0;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    image_to_uint8_bicubic_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        x, C, H, W, out, h0, w0, (float)H / (float)h0, (float)W / (float)w0);
     count_launch();
     SUPIR_CHECK_CUDA(cudaGetLastError());
     return SUPIR_OK;

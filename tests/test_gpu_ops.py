@@ -302,3 +302,19 @@ def test_colorfix_vs_reference_golden():
     close(lo.cpu(), torch.from_numpy(g["low"]), 2e-5, 1e-5)
     close(colorfix.wavelet_reconstruction(content.cuda(), style.cuda()).cpu(), torch.from_numpy(g["wavelet"]), 2e-5, 1e-5)
     close(colorfix.adaptive_instance_normalization(content.cuda(), style.cuda()).cpu(), torch.from_numpy(g["adain"]), 2e-5, 1e-5)
+
+
+def test_tensor2pil_bicubic_uint8_matches_torch():
+    """supir_image_to_uint8_bicubic vs the reference's Tensor2PIL arithmetic (SUPIR/util.py:87-94) computed by torch."""
+    from supir_b200 import util
+    x = (rnd((3, 96, 160), 77) * 0.6).clamp(-1.2, 1.2)
+    for h0, w0 in ((96, 160), (75, 131), (200, 333), (48, 80)):
+        ref = F.interpolate(x[None], size=(h0, w0), mode="bicubic")
+        ref = (ref[0].permute(1, 2, 0) * 127.5 + 127.5).numpy().clip(0, 255).astype(np.uint8)
+        got = util.tensor_to_uint8(x.cuda(), h0, w0).cpu().numpy()
+        assert got.shape == ref.shape and got.dtype == np.uint8
+        diff = np.abs(got.astype(np.int32) - ref.astype(np.int32))
+        # the truncation to uint8 turns a last-bit difference of the fp32 interpolation into one grey level now and then
+        assert diff.max() <= 1 and (diff != 0).mean() <= 2e-3, (h0, w0, int(diff.max()), float((diff != 0).mean()))
+        if (h0, w0) == (96, 160):
+            assert diff.max() == 0          # same size: the bicubic kernel is the identity

@@ -566,6 +566,18 @@ int main(int argc, char** argv) {
         }
         supir_set_gemm_pair_mode(1);
     }
+    if (what == "attnquick") {     // hang guard for a GPU session: every kernel variant once, small
+        for (int emu : {2, 0, 4}) {
+            supir_set_attention_exp_emulation(emu);
+            test_attention(1, 2, 128, 256, 0);
+            test_attention(2, 3, 200, 77, 0);
+            test_attention(1, 2, 333, 128, 0);
+            test_attention(1, 2, 333, 500, 0);
+            test_attention(40, 8, 512, 512, 200);     // 640 work items: the persistent loop wraps on every SM
+            test_attention(60, 8, 256, 77, 200);
+        }
+        supir_set_attention_exp_emulation(-1);
+    }
     if (what == "attn" || what == "all") {
       for (int emu : {0, 2, 4}) {
         printf("-- softmax exponent emulation %d of 4 pairs\n", emu);
