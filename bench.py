@@ -61,6 +61,10 @@ WORKLOADS = {
                  shards=False, images_per_gpu=1,
                  desc="1024x1024 input, upscale 2 -> 2048x2048 (4.19 MP), 50 EDM steps, untiled RestoreEDMSampler on the 256x256 "
                       "latent (16 384-token self-attention), CFG pair, untiled VAE; one image per GPU (replicas only)"),
+    "cfg2pair": dict(in_px=1024, upscale=2, sampler="RestoreEDMSampler", tile=None, stride=None, steps=50, enc_tile=None, dec_tile=None,
+                     shards=True, images_per_gpu=1,
+                     desc="cfg2 in latency mode: ONE 1024 -> 2048x2048 image on TWO GPUs, the unconditional / conditional CFG branch "
+                          "of every untiled step on its own GPU, one all-gather of the network outputs per step (VAE replicated)"),
     "cfg4": dict(in_px=2048, upscale=4, sampler="TiledRestoreEDMSampler", tile=128, stride=64, steps=50, enc_tile=512, dec_tile=64,
                  shards=True, images_per_gpu=1,
                  desc="2048x2048->8192x8192 (67.1 MP), 50 EDM steps, TiledRestoreEDMSampler 128/64 = 225 windows, CFG pair, tiled VAE "

@@ -39,6 +39,12 @@ typedef struct supir_epilogue {
     int act;                /* 0 none; 1 SiLU; 2 GEGLU (accumulator columns in groups of 32 = 16 value | 16 gate,      */
                             /*   output has N/2 columns; attention.py:84-92, exact-erf GELU)                            */
     int out_f32;            /* 1: out is fp32 instead of bf16                                                          */
+    /* LayerNorm folded into the GEMM (attention.py:465-486, norm -> Linear): with A the RAW (un-normalised) rows, W the weight  */
+    /* with gamma multiplied into its columns, and bias' = W beta + bias,                                                      */
+    /*   LN(a) W^T + bias = rstd * (a W'^T) - (mean * rstd) * colsum(W') + bias'                                               */
+    /* ln_stats: [M, 2] fp32 (rstd, mean * rstd) per row from supir_layernorm_stats; ln_colsum: [N] fp32. Both or neither.     */
+    const float* ln_stats;
+    const float* ln_colsum;
 } supir_epilogue;
 
 /* out[M, N] = epilogue(A[M, K] @ W[N, K]^T); A, W bf16 row-major with leading dims lda/ldw (elements, multiples of 8).
@@ -126,6 +132,10 @@ int supir_zerosft_apply(const void* h, long long ldh, const void* skip_raw, long
 /* nn.LayerNorm over the last dim (attention.py:437-439), eps 1e-5; C % 8 == 0, C <= 2048 */
 int supir_layernorm_bf16(const void* x, long long ldx, void* y, long long ldy, long long rows, int C, const float* gamma,
                          const float* beta, float eps, void* stream);
+/* per-row LayerNorm statistics only: stats[r] = (rstd, mean * rstd), for the GEMM epilogue's folded LayerNorm (one read
+ * pass instead of a read + write pass, and no normalised copy of the activations) */
+int supir_layernorm_stats(const void* x, long long ldx, long long rows, int C, float eps, float* stats, void* stream);
+
 /* P = softmax(S * scale) row-wise, fp32 -> bf16 (single-head 512-dim VAE attention, model.py:187-189) */
 int supir_softmax_rows(const float* S, long long lds, void* P, long long ldp, long long rows, int cols, float scale,
                        void* stream);

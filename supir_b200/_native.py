@@ -14,7 +14,7 @@ c_void_p, c_int, c_ll, c_float, c_double = ctypes.c_void_p, ctypes.c_int, ctypes
 class Epilogue(ctypes.Structure):
     """struct supir_epilogue (include/supir_b200.h)."""
     _fields_ = [("bias", c_void_p), ("rowvec", c_void_p), ("rows_per_batch", c_int), ("rowvec_ld", c_int),
-                ("residual", c_void_p), ("ldr", c_ll), ("act", c_int), ("out_f32", c_int)]
+                ("residual", c_void_p), ("ldr", c_ll), ("act", c_int), ("out_f32", c_int), ("ln_stats", c_void_p), ("ln_colsum", c_void_p)]
 
 
 # name -> argtypes (all return int unless listed in _SPECIAL)
@@ -36,6 +36,7 @@ _SIGS = {
     "supir_groupnorm_apply": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p],
     "supir_zerosft_apply": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p],
     "supir_layernorm_bf16": [c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p, c_void_p, c_float, c_void_p],
+    "supir_layernorm_stats": [c_void_p, c_ll, c_ll, c_int, c_float, c_void_p, c_void_p],
     "supir_softmax_rows": [c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_float, c_void_p],
     "supir_attention_bf16": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p],
     "supir_debug_set_attention_descriptors": [c_ll, c_ll],

@@ -56,6 +56,8 @@ struct GemmKernelParams {
     int nimg;             // conv mode: number of images (patches beyond it are padding of the last CTA pair)
     int staged;           // 1: epilogue through shared memory (bias tile in smem, TMA-loaded residual, TMA store)
     int has_res;          // staged path: residual tensor map valid
+    const float2* ln_stats;  // per-row (rstd, mean * rstd) of A: LayerNorm folded into the epilogue (see supir_epilogue), or null
+    const float* ln_colsum;  // [N] row sums of the (gamma-scaled) weight matrix
     int warp_epi;         // staged path: 1 = every epilogue warp moves ITS 32 rows with its own TMA operations (no named barriers)
     uint32_t desc_hi;     // upper 32 bits of the shared-memory matrix descriptor (SBO / version / swizzle mode)
     uint32_t desc_lbo;    // LBO field (bits 16..29 of the low word), pre-shifted
@@ -71,7 +73,7 @@ struct GemmSmem {
     // epilogue staging: per half-group (4 warps = 128 rows) two 8 KB output buffers and two 8 KB residual buffers
     // (128 rows x 32 bf16 columns, 64B-swizzled), plus the tile's bias (+ per-image vector) for both accumulators
     static constexpr int CH_BYTES = BM * 32 * 2;
-    static constexpr int EPI_BYTES = 8 * CH_BYTES + 2 * BN * 4;
+    static constexpr int EPI_BYTES = 8 * CH_BYTES + 4 * BN * 4;     // + bias and LayerNorm column-sum tiles for both accumulators
     static constexpr int ACC_STRIDE = (BN == 160) ? 256 : BN;          // TMEM column offset of the second accumulator
     static constexpr int TMEM_COLS = (BN == 160) ? 512 : 2 * BN;       // allocation must be a power of two
     static constexpr int BAR_BYTES = 512;
@@ -233,6 +235,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint8_t* stage_c = smem_epi + h * 2 * S::CH_BYTES;
         uint8_t* stage_r = smem_epi + 4 * S::CH_BYTES + h * 2 * S::CH_BYTES;
         float* s_bias = reinterpret_cast<float*>(smem_epi + 8 * S::CH_BYTES);
+        float* s_c1 = s_bias + 2 * BN;
         uint64_t* my_res_full = res_full + (wl ? 2 * (warp - 2) : 2 * h);
         // swizzled 16-byte chunk position inside a staging row (64B swizzle for 64-byte rows, 32B swizzle for GEGLU's 32-byte rows)
         const int row_bytes = geglu ? 32 : 64;
@@ -270,14 +273,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             };
             // tile prologue: bias (+ per-image vector) for the tile's columns; first two residual chunks
             float* sb = s_bias + acc * BN;
+            float* sc = s_c1 + acc * BN;
             if (epi_tid < BN) {
                 const int n = nt * BN + epi_tid;
-                float b = 0.f;
+                float b = 0.f, c1 = 0.f;
                 if (n < p.N) {
                     if (p.bias) b = __ldg(p.bias + n);
                     if (p.rowvec && cb < p.nimg) b += __ldg(p.rowvec + (long long)cb * p.rowvec_ld + n);
+                    if (p.ln_colsum) c1 = __ldg(p.ln_colsum + n);
                 }
                 sb[epi_tid] = b;
+                sc[epi_tid] = c1;
+            }
+            // folded LayerNorm: out = rstd * acc - (mean * rstd) * colsum + bias', one (rstd, mean * rstd) pair per row
+            float ln_rs = 1.f, ln_nm = 0.f;
+            if (p.ln_stats) {
+                const long long grow = (long long)rt * BM + row;
+                if (grow < p.M) { const float2 st = __ldg(p.ln_stats + grow); ln_rs = st.x; ln_nm = -st.y; }
             }
             named_bar_sync(5, 256);
             if (p.has_res && elected) {
@@ -293,6 +305,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int c = h + 2 * k;
                 const int buf = (cnt + k) & 1;
                 const float* bc = sb + c * 32;
+                const float* cc = sc + c * 32;
                 uint4 q[4];
                 if (geglu) {
                     float o[16], bb[32];
@@ -308,6 +321,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     q[1] = make_uint4(pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]), pack_bf16x2(o[12], o[13]), pack_bf16x2(o[14], o[15]));
                 } else {
                     float v[32];
+                    if (p.ln_stats) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(bc + j);
+                            const float4 c4 = *reinterpret_cast<const float4*>(cc + j);
+                            v[j] = fmaf(__uint_as_float(r[j]), ln_rs, fmaf(ln_nm, c4.x, b4.x));
+                            v[j + 1] = fmaf(__uint_as_float(r[j + 1]), ln_rs, fmaf(ln_nm, c4.y, b4.y));
+                            v[j + 2] = fmaf(__uint_as_float(r[j + 2]), ln_rs, fmaf(ln_nm, c4.z, b4.z));
+                            v[j + 3] = fmaf(__uint_as_float(r[j + 3]), ln_rs, fmaf(ln_nm, c4.w, b4.w));
+                        }
+                    } else {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 b4 = *reinterpret_cast<const float4*>(bc + j);
@@ -315,6 +339,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
                         v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
                         v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+                    }
                     }
                     if (p.act == 1) {
 #pragma unroll
@@ -417,6 +442,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    if (p.ln_stats) {
+                        const float2 st = __ldg(p.ln_stats + grow);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (n0 + j < p.N) v[j] = fmaf(v[j], st.x, -st.y * __ldg(p.ln_colsum + n0 + j));
+                    }
                     if (p.bias) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
@@ -800,7 +831,13 @@ static int run_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmKernelPa
 static int fill_epilogue(GemmKernelParams& p, const supir_epilogue* ep, int N) {
     p.bias = nullptr; p.rowvec = nullptr; p.rows_per_batch = 0; p.rowvec_ld = 0;
     p.residual = nullptr; p.ldr = 0; p.act = 0; p.out_f32 = 0; p.n_out = N;
+    p.ln_stats = nullptr; p.ln_colsum = nullptr;
     if (ep) {
+        p.ln_stats = reinterpret_cast<const float2*>(ep->ln_stats);
+        p.ln_colsum = ep->ln_colsum;
+        SUPIR_REQUIRE((p.ln_stats == nullptr) == (p.ln_colsum == nullptr), "epilogue: ln_stats and ln_colsum go together");
+        SUPIR_REQUIRE(!p.ln_stats || (ep->act != 2 && !p.conv), "folded LayerNorm is for plain GEMM epilogues (not GEGLU, not conv)");
+        SUPIR_REQUIRE(!p.ln_stats || (reinterpret_cast<uintptr_t>(ep->ln_stats) & 7) == 0, "ln_stats must be 8-byte aligned");
         p.bias = ep->bias;
         p.rowvec = ep->rowvec;
         p.rows_per_batch = ep->rows_per_batch;

@@ -262,7 +262,7 @@ __global__ void sft_apply_kernel(const __nv_bfloat16* __restrict__ h, long long 
 template <int MAXV>  // max 16-byte vectors per lane
 __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y,
                                  long long ldy, long long rows, int C, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, float eps) {
+                                 const float* __restrict__ beta, float eps, float2* __restrict__ stats) {
     const int lane = threadIdx.x & 31;
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
     long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -311,6 +311,10 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long 
             }
         }
         const float rstd = rsqrtf(warp_sum(q) / C + eps);
+        if (stats) {                                   // statistics only (LayerNorm folded into the consumer GEMM's epilogue)
+            if (lane == 0) stats[row] = make_float2(rstd, mean * rstd);
+            continue;
+        }
 #pragma unroll
         for (int i = 0; i < MAXV; ++i) {
             const int vi = lane + i * 32;
@@ -517,10 +521,25 @@ extern "C" int supir_zerosft_apply(const void* h, long long ldh, const void* ski
     return SUPIR_OK;
 }
 
+static int launch_layernorm(const void* x, long long ldx, void* y, long long ldy, long long rows, int C, const float* gamma,
+                            const float* beta, float eps, float2* stats, void* stream);
+
+extern "C" int supir_layernorm_stats(const void* x, long long ldx, long long rows, int C, float eps, float* stats, void* stream) {
+    SUPIR_REQUIRE(x && stats && rows > 0, "supir_layernorm_stats: bad args");
+    SUPIR_REQUIRE(C % 8 == 0 && C <= 2048 && ldx % 8 == 0, "supir_layernorm_stats: unsupported C=%d", C);
+    SUPIR_REQUIRE((reinterpret_cast<uintptr_t>(stats) & 7) == 0, "supir_layernorm_stats: stats must be 8-byte aligned");
+    return launch_layernorm(x, ldx, nullptr, 0, rows, C, nullptr, nullptr, eps, reinterpret_cast<float2*>(stats), stream);
+}
+
 extern "C" int supir_layernorm_bf16(const void* x, long long ldx, void* y, long long ldy, long long rows, int C,
                                     const float* gamma, const float* beta, float eps, void* stream) {
     SUPIR_REQUIRE(x && y && gamma && beta, "supir_layernorm_bf16: null pointer");
     SUPIR_REQUIRE(C % 8 == 0 && C <= 2048 && ldx % 8 == 0 && ldy % 8 == 0, "supir_layernorm_bf16: unsupported C=%d", C);
+    return launch_layernorm(x, ldx, y, ldy, rows, C, gamma, beta, eps, nullptr, stream);
+}
+
+static int launch_layernorm(const void* x, long long ldx, void* y, long long ldy, long long rows, int C, const float* gamma,
+                            const float* beta, float eps, float2* stats, void* stream) {
     const int warps = 8;
     long long blocks = (rows + warps - 1) / warps;
     const long long cap = (long long)device_sm_count() * 16;       // a few resident waves; warps then loop over rows
@@ -530,11 +549,11 @@ extern "C" int supir_layernorm_bf16(const void* x, long long ldx, void* y, long 
     __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
     const int nv = C >> 3;
     if (nv <= 96)
-        layernorm_kernel<3><<<(unsigned)blocks, warps * 32, 0, st>>>(xp, ldx, yp, ldy, rows, C, gamma, beta, eps);
+        layernorm_kernel<3><<<(unsigned)blocks, warps * 32, 0, st>>>(xp, ldx, yp, ldy, rows, C, gamma, beta, eps, stats);
     else if (nv <= 160)
-        layernorm_kernel<5><<<(unsigned)blocks, warps * 32, 0, st>>>(xp, ldx, yp, ldy, rows, C, gamma, beta, eps);
+        layernorm_kernel<5><<<(unsigned)blocks, warps * 32, 0, st>>>(xp, ldx, yp, ldy, rows, C, gamma, beta, eps, stats);
     else
-        layernorm_kernel<8><<<(unsigned)blocks, warps * 32, 0, st>>>(xp, ldx, yp, ldy, rows, C, gamma, beta, eps);
+        layernorm_kernel<8><<<(unsigned)blocks, warps * 32, 0, st>>>(xp, ldx, yp, ldy, rows, C, gamma, beta, eps, stats);
     count_launch();
     SUPIR_CHECK_CUDA(cudaGetLastError());
     return SUPIR_OK;

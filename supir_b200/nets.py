@@ -7,11 +7,17 @@ path: `pack()` converts the weights once into the kernel layouts (bf16, K-major,
 matrices, fp32 biases) and `run()` issues hand-written sm_100a kernels through the C ABI (supir_b200/ops.py) on
 channels-last bf16 activations. Options the SUPIR configs never use raise NotImplementedError.
 """
+import os
+
 import torch
 import torch.nn as nn
 
 from . import ops
 from .ops import BF16
+
+# LayerNorm -> Linear pairs (norm1 -> QKV, norm2 -> to_q) run as ONE statistics pass + a GEMM whose epilogue applies the
+# normalisation (ops.fold_layernorm); "0" restores the stand-alone LayerNorm kernel in front of those GEMMs.
+FUSE_LN = os.environ.get("SUPIR_B200_FUSE_LN", "1") != "0"
 
 GN_EPS_UNET = 1e-5   # GroupNorm32 (sgm/modules/diffusionmodules/util.py:258-276)
 GN_EPS_ATTN = 1e-6   # attention.Normalize (sgm/modules/attention.py:122-125)
@@ -228,19 +234,37 @@ class CrossAttention(nn.Module):
         self.to_out = nn.Sequential(nn.Linear(inner, query_dim), nn.Dropout(dropout))
         self.kv_offset = None   # column offset inside Ctx.ctx_kv for text cross-attention
 
+    _ln = None      # (gamma, beta) of the LayerNorm in front of the query projection, set by BasicTransformerBlock.pack
+
     def pack(self):
         if self.is_self:
-            self._wqkv = _bf(torch.cat([self.to_q.weight, self.to_k.weight, self.to_v.weight], 0))
+            wqkv = torch.cat([self.to_q.weight, self.to_k.weight, self.to_v.weight], 0)
+            if self._ln is not None:
+                self._wqkv, self._c1, self._bq = ops.fold_layernorm(wqkv, None, *self._ln)
+            else:
+                self._wqkv, self._c1, self._bq = _bf(wqkv), None, None
         else:
-            self._wq = _bf(self.to_q.weight)
+            if self._ln is not None:
+                self._wq, self._c1, self._bq = ops.fold_layernorm(self.to_q.weight, None, *self._ln)
+            else:
+                self._wq, self._c1, self._bq = _bf(self.to_q.weight), None, None
             self._wkv = _bf(torch.cat([self.to_k.weight, self.to_v.weight], 0))
         self._wo, self._bo = _bf(self.to_out[0].weight), _bias_bf16_values(self.to_out[0].bias)
 
-    def run_self(self, ctx, xn, x_res, B, L):
-        """x_res + to_out(attn(xn)); xn, x_res: [B*L, C]."""
+    def _ln_args(self, stats):
+        """gemm() keywords of the query-side projection: folded LayerNorm when this module was packed with one."""
+        if self._c1 is None:
+            assert stats is None, "this CrossAttention was packed without a folded LayerNorm: pass normalised activations"
+            return {}
+        assert stats is not None, "this CrossAttention folds its LayerNorm: pass the raw activations and their row statistics"
+        return dict(bias=self._bq, ln=(stats, self._c1))
+
+    def run_self(self, ctx, xn, x_res, B, L, stats=None):
+        """x_res + to_out(attn(xn)); xn, x_res: [B*L, C]. With a folded LayerNorm xn is the RAW input and `stats` its row
+        statistics (ops.layernorm_stats)."""
         C = self.inner
         qkv = ctx.new(B * L, 3 * C)
-        ops.gemm(xn, self._wqkv, qkv)
+        ops.gemm(xn, self._wqkv, qkv, **self._ln_args(stats))
         a = ctx.new(B * L, C)
         ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], a, B, self.heads, L, L)
         ctx.free(qkv)
@@ -249,10 +273,10 @@ class CrossAttention(nn.Module):
         ctx.free(a)
         return out
 
-    def run_cross(self, ctx, xn, x_res, B, L, k, v, Lk, residual=True):
+    def run_cross(self, ctx, xn, x_res, B, L, k, v, Lk, residual=True, stats=None):
         C = self.inner
         q = ctx.new(B * L, C)
-        ops.gemm(xn, self._wq, q)
+        ops.gemm(xn, self._wq, q, **self._ln_args(stats))
         a = ctx.new(B * L, C)
         ops.attention(q, k, v, a, B, self.heads, L, Lk)
         ctx.free(q)
@@ -311,16 +335,31 @@ class BasicTransformerBlock(nn.Module):
     def pack(self):
         for n in (self.norm1, self.norm2, self.norm3):
             pack_norm(n)
+        # norm1 -> QKV and norm2 -> to_q are folded into those GEMMs (runs before the children's pack(): modules() yields
+        # parents first). norm3 stays a kernel: its consumer is the GEGLU GEMM, whose epilogue is already the bound.
+        self.fuse_ln = FUSE_LN
+        self.attn1._ln = (self.norm1.weight, self.norm1.bias) if self.fuse_ln else None
+        self.attn2._ln = (self.norm2.weight, self.norm2.bias) if self.fuse_ln else None
 
     def run(self, ctx, x, B, L):
-        n = ctx.new(*x.shape)
-        ops.layernorm(x, n, self.norm1._w, self.norm1._b)
-        x1 = self.attn1.run_self(ctx, n, x, B, L)
-        ctx.free(x)
-        ops.layernorm(x1, n, self.norm2._w, self.norm2._b)
         C = self.attn2.inner
         off = self.attn2.kv_offset
-        x2 = self.attn2.run_cross(ctx, n, x1, B, L, ctx.ctx_kv[:, off:off + C], ctx.ctx_kv[:, off + C:off + 2 * C], ctx.Lctx)
+        k, v = ctx.ctx_kv[:, off:off + C], ctx.ctx_kv[:, off + C:off + 2 * C]
+        n = ctx.new(*x.shape)
+        if self.fuse_ln:
+            st = ctx.pool.get((x.shape[0], 2), torch.float32)
+            ops.layernorm_stats(x, st, self.norm1.eps)
+            x1 = self.attn1.run_self(ctx, x, x, B, L, stats=st)
+            ctx.free(x)
+            ops.layernorm_stats(x1, st, self.norm2.eps)
+            x2 = self.attn2.run_cross(ctx, x1, x1, B, L, k, v, ctx.Lctx, stats=st)
+            ctx.pool.put(st)
+        else:
+            ops.layernorm(x, n, self.norm1._w, self.norm1._b)
+            x1 = self.attn1.run_self(ctx, n, x, B, L)
+            ctx.free(x)
+            ops.layernorm(x1, n, self.norm2._w, self.norm2._b)
+            x2 = self.attn2.run_cross(ctx, n, x1, B, L, k, v, ctx.Lctx)
         ctx.free(x1)
         ops.layernorm(x2, n, self.norm3._w, self.norm3._b)
         x3 = self.ff.run(ctx, n, x2)

@@ -64,8 +64,10 @@ class Pool:
 # ------------------------------------------------------------------------------------------------------------------
 # tensor-core ops
 # ------------------------------------------------------------------------------------------------------------------
-def _epilogue(bias, rowvec, rows_per_batch, residual, act, out_f32):
+def _epilogue(bias, rowvec, rows_per_batch, residual, act, out_f32, ln=None):
     ep = Epilogue()
+    ep.ln_stats = None if ln is None else ln[0].data_ptr()
+    ep.ln_colsum = None if ln is None else ln[1].data_ptr()
     ep.bias = None if bias is None else bias.data_ptr()
     ep.rowvec = None if rowvec is None else rowvec.data_ptr()
     ep.rows_per_batch = int(rows_per_batch)
@@ -77,14 +79,18 @@ def _epilogue(bias, rowvec, rows_per_batch, residual, act, out_f32):
     return ep
 
 
-def gemm(a, w, out, bias=None, rowvec=None, rows_per_batch=0, residual=None, act=0):
-    """out[M, N'] = epilogue(a[M, K] @ w[N, K]^T); N' = N/2 for act=2 (GEGLU). `out` may be fp32 or bf16."""
+def gemm(a, w, out, bias=None, rowvec=None, rows_per_batch=0, residual=None, act=0, ln=None):
+    """out[M, N'] = epilogue(a[M, K] @ w[N, K]^T); N' = N/2 for act=2 (GEGLU). `out` may be fp32 or bf16.
+    `ln=(stats, colsum)` folds a LayerNorm of `a` into the epilogue (see supir_epilogue in include/supir_b200.h): `a` is the
+    raw activation, `w` carries gamma, `bias` carries W beta + bias, stats comes from layernorm_stats()."""
     _need_cuda(a, w, out)
     _mat(a), _mat(w)
     M, K = a.shape
     N = w.shape[0]
     assert w.shape[1] == K and out.shape[0] == M and out.shape[1] == (N // 2 if act == 2 else N), (a.shape, w.shape, out.shape)
-    ep = _epilogue(bias, rowvec, rows_per_batch, residual, act, out.dtype == torch.float32)
+    if ln is not None:
+        assert ln[0].dtype == torch.float32 and ln[0].shape == (M, 2) and ln[0].is_contiguous() and ln[1].shape == (N,)
+    ep = _epilogue(bias, rowvec, rows_per_batch, residual, act, out.dtype == torch.float32, ln)
     call("supir_gemm_bf16", _ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(out), out.stride(0), M, N, K,
          ctypes.byref(ep), _stream())
     return out
@@ -164,6 +170,26 @@ def layernorm(x, out, gamma, beta, eps=1e-5):
     call("supir_layernorm_bf16", _ptr(x), x.stride(0), _ptr(out), out.stride(0), x.shape[0], x.shape[1], _ptr(gamma),
          _ptr(beta), float(eps), _stream())
     return out
+
+
+def layernorm_stats(x, stats, eps=1e-5):
+    """stats[r] = (rstd, mean * rstd) of row r of x (fp32 [rows, 2]) for gemm(..., ln=(stats, colsum))."""
+    _need_cuda(x, stats)
+    _mat(x)
+    assert stats.dtype == torch.float32 and stats.shape == (x.shape[0], 2) and stats.is_contiguous()
+    call("supir_layernorm_stats", _ptr(x), x.stride(0), x.shape[0], x.shape[1], float(eps), _ptr(stats), _stream())
+    return stats
+
+
+def fold_layernorm(w, bias, gamma, beta):
+    """Weights of `Linear(LayerNorm(x))` for the folded form: (bf16 W * gamma, fp32 colsum of that, fp32 W beta + bias)."""
+    wf = w.detach().to(BF16).to(torch.float32)                 # the values the reference's bf16 matmul sees
+    wg = (wf * gamma.detach().to(torch.float32)[None, :]).to(BF16).contiguous()
+    colsum = wg.to(torch.float32).sum(dim=1).contiguous()
+    b2 = wf @ beta.detach().to(torch.float32)
+    if bias is not None:
+        b2 = b2 + bias.detach().to(BF16).to(torch.float32)
+    return wg, colsum, b2.contiguous()
 
 
 def softmax_rows(S, P, cols, scale):

@@ -127,6 +127,9 @@ class BaseDiffusionSampler:
 
 
 class RestoreEDMSampler(BaseDiffusionSampler):
+    shard = False            # opt-in: run the two CFG branches of an untiled step on two torch.distributed ranks (_EDMRun)
+    process_group = None
+
     def __init__(self, s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0, restore_cfg=4.0, restore_cfg_s_tmin=0.05,
                  *args, **kwargs):
         super().__init__(*args, **kwargs)
@@ -211,9 +214,23 @@ class RestoreEDMSampler(BaseDiffusionSampler):
 
 
 class _EDMRun:
+    """One untiled sampling run. With `smp.shard` set on a 2-rank group (opt-in, identical inputs and RNG state on both
+    ranks) the two CFG branches of every step run on different GPUs — rank 0 the unconditional rows, rank 1 the
+    conditional ones (halves the latency of an untiled image) — with ONE all-gather of the raw
+    network outputs per step; both ranks then finish the step, so x stays bit-identical on both and equal to the
+    single-GPU result."""
+
     def __init__(self, smp, denoiser, x, cond, uc, num_steps, x_center, control_scale, lin_cs, cs_start):
+        import torch.distributed as dist
         self.smp, self.denoiser, self.cond, self.uc = smp, denoiser, cond, uc
         self.uid = next(_RUN_IDS)
+        self.group = getattr(smp, "process_group", None)
+        fused = isinstance(denoiser, FusedDenoiser) and hasattr(smp.guider, "scale_host")
+        self.world, self.rank = ((dist.get_world_size(self.group), dist.get_rank(self.group))
+                                 if getattr(smp, "shard", False) and fused and dist.is_available() and dist.is_initialized() else (1, 0))
+        if self.world > 1:
+            self.per, self.lo, self.hi = shard_units(2, self.world, self.rank)       # units = the two CFG branches
+            self.pair_out = torch.zeros((self.per * self.world,) + tuple(x.shape), dtype=torch.float32, device=x.device)
         self.control_scale, self.lin_cs, self.cs_start = control_scale, lin_cs, cs_start
         self.x, self.sigmas = smp.prepare_sampling_loop(x, num_steps)
         self.xc = None if x_center is None else x_center.contiguous().float()
@@ -224,8 +241,36 @@ class _EDMRun:
         k = self.smp.step_constants(self.sigmas, i, self.control_scale, self.lin_cs, self.cs_start)
         k["context_token"] = self.uid          # cond / uc are this run's, unchanged over its steps
         eps = torch.randn_like(self.x) if k["gamma"] > 0 else None
-        self.x = self.smp._step(self.denoiser, self.x, eps, self.cond, self.uc, self.xc, k)
+        if self.world > 1:
+            self.x = self._step_branch_parallel(k, eps)
+        else:
+            self.x = self.smp._step(self.denoiser, self.x, eps, self.cond, self.uc, self.xc, k)
         return self.x
+
+    def _step_branch_parallel(self, k, eps):
+        smp, x = self.smp, self.x
+        N = x.shape[0]
+        sq, idx = self.denoiser.denoiser.quantize_host(k["sigma_hat"])
+        c_in = float(f32(1.0) / np.sqrt(f32(sq) * f32(sq) + f32(1.0)))
+        x_hat = torch.empty_like(x)
+        net_in = torch.empty((2 * N,) + tuple(x.shape[1:]), dtype=torch.float32, device=x.device)
+        ops.edm_pre(x, eps if k["gamma"] > 0 else None, k["noise_mul"], c_in, x_hat, net_in)
+        for u in range(self.lo, self.hi):            # unit 0: unconditional rows, unit 1: conditional rows
+            c = self.uc if u == 0 else self.cond
+            t = torch.full((N,), idx, dtype=torch.long, device=x.device)
+            out = self.denoiser.network(net_in[u * N:(u + 1) * N], t, {key: c[key] for key in ("vector", "crossattn", "control")},
+                                        k["control_scale"], context_token=(self.uid, u))
+            self.pair_out[self.rank * self.per + (u - self.lo)] = out
+        exchange_unit_outputs(self.pair_out, self.rank, self.per, self.group)
+        if self.per * self.world == 2:
+            both = self.pair_out
+        else:                                         # more than two ranks: the first two carry one branch each
+            both = torch.stack([self.pair_out[r * self.per] for r, (_, lo, hi) in
+                                enumerate(shard_units(2, self.world, q) for q in range(self.world)) if hi > lo], 0)
+        x_next = torch.empty_like(x)
+        ops.edm_post(x_hat, both.reshape((2 * N,) + tuple(x.shape[1:])), self.xc if k["use_restore"] else None, -sq,
+                     smp.guider.scale_host(k["sigma_hat"]), k["restore_mul"], k["sigma_hat"], k["dt"], x_next)
+        return x_next
 
 
 class TiledRestoreEDMSampler(RestoreEDMSampler):

@@ -25,3 +25,4 @@ def test_sharded_sampler_and_vae_bit_identical_to_single_gpu():
     res = json.loads(line)
     print(res)
     assert res["sampler_sharded_equals_single"] and res["identical_on_all_ranks"] and res["vae_sharded_equals_single"]
+    assert res["untiled_branch_parallel_equals_single"]

@@ -318,3 +318,34 @@ def test_tensor2pil_bicubic_uint8_matches_torch():
         assert diff.max() <= 1 and (diff != 0).mean() <= 2e-3, (h0, w0, int(diff.max()), float((diff != 0).mean()))
         if (h0, w0) == (96, 160):
             assert diff.max() == 0          # same size: the bicubic kernel is the identity
+
+
+@pytest.mark.parametrize("M,C,N,with_res", [(3000, 640, 1920, False), (1111, 1280, 1280, True), (129, 320, 96, False)])
+def test_gemm_with_folded_layernorm(M, C, N, with_res):
+    """Linear(LayerNorm(x)) as statistics pass + GEMM with the normalisation in its epilogue (attention.py:465-486) vs torch fp32."""
+    ops = _ops()
+    x = (rnd((M, C), 91) * 1.7 + 0.4).to(BF)
+    w = rnd((N, C), 92) / C ** 0.5
+    g, b = rnd((C,), 93) * 0.2 + 1, rnd((C,), 94) * 0.2
+    bias = rnd((N,), 95) * 0.1
+    res = rnd((M, N), 96).to(BF) if with_res else None
+    ref = F.layer_norm(x.float(), (C,), g, b, 1e-5).to(BF).float() @ w.to(BF).float().t() + bias.to(BF).float()
+    if res is not None:
+        ref = ref.to(BF).float() + res.float()
+    wg, c1, b2 = ops.fold_layernorm(w.cuda(), bias.cuda(), g.cuda(), b.cuda())
+    stats = torch.empty(M, 2, dtype=torch.float32, device="cuda")
+    ops.layernorm_stats(x.cuda(), stats)
+    xf = x.float()
+    rstd = (xf.var(1, unbiased=False) + 1e-5).rsqrt()
+    close(stats[:, 0].cpu(), rstd, 1e-4, 1e-4)
+    close(stats[:, 1].cpu(), xf.mean(1) * rstd, 1e-4, 1e-4)
+    from supir_b200 import _native
+    lib = _native.load()
+    try:
+        for direct in (0, 1):
+            lib.supir_debug_force_direct_epilogue(direct)
+            out = torch.empty(M, N, dtype=BF, device="cuda")
+            ops.gemm(x.cuda(), wg, out, bias=b2, residual=None if res is None else res.cuda(), ln=(stats, c1))
+            close(out.float().cpu(), ref, 4e-2, 3e-2)
+    finally:
+        lib.supir_debug_force_direct_epilogue(0)

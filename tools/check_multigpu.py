@@ -41,6 +41,17 @@ def main():
     a = run(True)
     b = run(False)
     same = torch.equal(a, b)
+
+    def run_untiled(shard):      # CFG-branch parallelism of the untiled sampler (ranks 0 / 1 carry one branch each)
+        smp = sampling.RestoreEDMSampler(num_steps=3, restore_cfg=4.0, s_churn=5, s_noise=1.01, discretization_config=disc,
+                                         guider_config={"target": "sgm.modules.diffusionmodules.guiders.LinearCFG", "params": {"scale": 1.0, "scale_min": 4.0}})
+        smp.shard = shard
+        torch.manual_seed(9)
+        x = randn((1, 4, 48, 40), 11).cuda()
+        c = {"control": randn((1, 4, 48, 40), 12).cuda(), "crossattn": randn((1, 77, 2048), 13).cuda(), "vector": randn((1, 2816), 14).cuda()}
+        uc = {"control": c["control"], "crossattn": randn((1, 77, 2048), 15).cuda(), "vector": randn((1, 2816), 16).cuda()}
+        return smp(denoiser, x, cond=c, uc=uc, x_center=randn((1, 4, 48, 40), 17).cuda(), control_scale=0.9)
+    pair_same = torch.equal(run_untiled(True), run_untiled(False))
     gathered = [torch.empty_like(a) for _ in range(world)]
     dist.all_gather(gathered, a)
     same_ranks = all(torch.equal(gathered[0], t) for t in gathered)
@@ -56,10 +67,10 @@ def main():
     ref = torch.from_numpy(gv["dec_tiled"]).cuda()
     rel = float((d_sharded - ref).norm() / ref.norm())
     if rank == 0:
-        print(json.dumps({"world": world, "sampler_sharded_equals_single": same, "identical_on_all_ranks": same_ranks,
+        print(json.dumps({"world": world, "sampler_sharded_equals_single": same, "untiled_branch_parallel_equals_single": pair_same, "identical_on_all_ranks": same_ranks,
                           "vae_sharded_rel_fro_vs_reference": rel, "vae_sharded_equals_single": vae_same, "finite": bool(torch.isfinite(a).all())}))
     dist.barrier()
     dist.destroy_process_group()
-    assert same and same_ranks and vae_same and rel < 3e-2
+    assert same and pair_same and same_ranks and vae_same and rel < 3e-2
 
 main()
