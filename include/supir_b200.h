@@ -149,6 +149,12 @@ int supir_softmax_rows(const float* S, long long lds, void* P, long long ldp, lo
 int supir_attention_bf16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                          void* out, long long ldo, int B, int H, int Lq, int Lk, int head_dim, float scale, void* stream);
 int supir_debug_set_attention_descriptors(long long smem_desc_template, long long idesc_pv);
+/* Single-head attention with a wide head over L tokens per batch element (the SDXL VAE mid-block AttnBlock, head_dim 512:
+ * model.py:158-206, 209-262; tilevae.py:292-336; 128 / 256 for reduced-width VAE configurations):
+ * out[b, i, 0:head_dim] = softmax(q k^T * scale) v. q/k/v/out: [B*L, ld] bf16, ld >= head_dim. Flash-style (no score matrix
+ * in HBM); at head_dim 512 the two halves of the value columns run as separate CTAs. */
+int supir_attention_1head_bf16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                               void* out, long long ldo, int B, int L, int head_dim, float scale, void* stream);
 /* tuning knob: how many of every 4 element pairs of the softmax take 2^x from the FMA-pipe polynomial instead of MUFU.EX2
  * (0..4; default 2 or the environment variable SUPIR_B200_ATTN_EMU; negative restores the default). */
 int supir_set_attention_exp_emulation(int pairs_of_4);

@@ -53,33 +53,6 @@ struct AttnParams {
     int nqb, num_items;    // query blocks per (batch, head); nqb * H * B work items
 };
 
-// ---------------------------------------------------------------------------------------------------------------------
-// packed fp32 pairs (sm_100 FFMA2 / FADD2: two fp32 operations per issue slot)
-// ---------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
-    uint64_t r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
-    uint64_t d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
-    uint64_t d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-__device__ __forceinline__ uint64_t fadd2_rm(uint64_t a, uint64_t b) {   // round towards -inf
-    uint64_t d;
-    asm("add.rm.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-
 // 2^x for a pair, x <= ~100, on the FMA / ALU pipes (no MUFU). x is clamped at -126 (result 2^-126 ~ 0 for anything below,
 // including the -inf of masked keys).
 __device__ __forceinline__ void ex2_emulated_pair(uint64_t x, float& e0, float& e1) {
@@ -499,7 +472,7 @@ extern "C" int supir_attention_bf16(const void* q, long long ldq, const void* k,
                                     long long ldv, void* out, long long ldo, int B, int H, int Lq, int Lk, int head_dim,
                                     float scale, void* stream) {
     SUPIR_REQUIRE(q && k && v && out, "supir_attention_bf16: null pointer");
-    SUPIR_REQUIRE(head_dim == 64, "supir_attention_bf16: head_dim %d unsupported (64 only; the VAE's single 512-wide head is supir_attention_d512_bf16)", head_dim);
+    SUPIR_REQUIRE(head_dim == 64, "supir_attention_bf16: head_dim %d unsupported (64 only; the VAE's single wide head is supir_attention_1head_bf16)", head_dim);
     SUPIR_REQUIRE(B > 0 && H > 0 && Lq > 0 && Lk > 0, "supir_attention_bf16: bad shape");
     SUPIR_REQUIRE(scale > 0.f, "supir_attention_bf16: scale must be positive");
     SUPIR_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "supir_attention_bf16: leading dims must be multiples of 8");
@@ -535,4 +508,306 @@ extern "C" int supir_attention_bf16(const void* q, long long ldq, const void* k,
     if (short_keys) return launch_attention_emu<1, 2, 96>(tmQ, tmK, tmV, p, B, st);
     if (Lk <= ATT_BN) return launch_attention_emu<1, 2, 128>(tmQ, tmK, tmV, p, B, st);
     return launch_attention_emu<2, 4, 128>(tmQ, tmK, tmV, p, B, st);
+}
+
+// =====================================================================================================================
+// Single-head attention with head_dim 512: the SDXL VAE's mid-block AttnBlock (sgm/modules/diffusionmodules/model.py:
+// 158-206 / MemoryEfficientAttnBlock :209-262; per tile in SUPIR/utils/tilevae.py:292-336): softmax(q k^T / sqrt(512)) v over
+// ALL pixels of a (tile's) 8x-downsampled feature map (18 496 tokens for a 1088-px encoder tile, 22 500 for a 150-latent
+// decoder tile). Flash-style: the score matrix never leaves the SM (round 1 wrote it to HBM in fp32: 1.4 GB per tile).
+//
+// The 512-wide output does not fit TMEM next to S (512 fp32 columns = all of it), so a CTA owns 128 queries and ONE HALF of
+// the value columns (grid.y = 2): O[128 x 256] in TMEM columns [0, 256), two S buffers [256, 384) / [384, 512); the bf16
+// probabilities overwrite the first 64 columns of the S buffer they came from (P aliases S), so QK of block j+1 runs on the
+// tensor pipe while the softmax warps work on block j. QK^T is recomputed by both halves (1.5x the minimal FLOPs) — cheaper
+// than moving S between SMs. Q (128 x 512 bf16 = 128 KB) stays resident in shared memory as 8 K-major 64-column chunks;
+// K and V stream through one ring of 16 KB slots: 8 K chunks (64 of the 512 depth each) and 4 V chunks (64 value columns each,
+// MN-major B operand straight from the [token, channel] layout) per 128-key block, in the order the MMA thread consumes them.
+// 256 threads: warp 0 TMA producer, warp 1 MMA issuer, warps 4..7 softmax (one query row per thread), same packed-fp32 /
+// partial-emulation exponential and lazy rescale as the head_dim-64 kernel.
+// =====================================================================================================================
+namespace supir {
+
+static constexpr int A5_SLOTS = 5;
+
+// D = head dim (512 for the SDXL VAE; 128 / 256 serve the reduced-width VAE configurations of the golden fixtures):
+// D / 64 depth chunks per QK, min(D, 256) value columns per CTA.
+template <int D>
+struct Attn512Smem {
+    static constexpr int NCH = D / 64;                            // 64-wide depth chunks of Q / K
+    static constexpr int DV = D > 256 ? 256 : D;                  // value columns owned by one CTA
+    static constexpr int CHUNK = ATT_BM * 64 * 2;                 // 16 KB: 128 rows x 64 bf16
+    static constexpr int OFF_Q = 0;                               // NCH chunks
+    static constexpr int OFF_RING = OFF_Q + NCH * CHUNK;
+    static constexpr int OFF_BAR = OFF_RING + A5_SLOTS * CHUNK;
+    static constexpr int TOTAL = OFF_BAR + 256 + 1024;
+};
+
+struct Attn512Params {
+    int L;
+    long long ldo;
+    __nv_bfloat16* out;
+    float scale_log2;
+    uint32_t desc_hi, idesc_qk, idesc_pv;
+};
+
+template <int D, int EMU>
+__global__ void __launch_bounds__(256, 1)
+attention_d512_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, const Attn512Params p) {
+    using SM = Attn512Smem<D>;
+    constexpr int NCH = SM::NCH, A5_DV = SM::DV, NVC = SM::DV / 64;
+    constexpr uint32_t COL_S = 256;                                // S buffer b at columns COL_S + 128 b
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem + SM::OFF_Q;
+    uint8_t* ring = smem + SM::OFF_RING;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
+    uint64_t* q_full = bars;                            // 1
+    uint64_t* slot_full = bars + 1;                     // [A5_SLOTS]
+    uint64_t* slot_empty = slot_full + A5_SLOTS;        // [A5_SLOTS]
+    uint64_t* s_full = slot_empty + A5_SLOTS;           // [2] per S buffer
+    uint64_t* p_full = s_full + 2;                      // [2]
+    uint64_t* pv_done = p_full + 2;                     // 1
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * ATT_BM, half = blockIdx.y, batch = blockIdx.z;
+    const int nblk = (p.L + ATT_BN - 1) / ATT_BN;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < A5_SLOTS; ++s) { mbar_init(&slot_full[s], 1); mbar_init(&slot_empty[s], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); }
+        mbar_init(pv_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp < 4) {
+      // (no setmaxnreg here: 256 threads at one CTA per SM can have 255 registers each as launched)
+      if (warp == 0) {
+        if (lane == 0) {
+            // ---------------- TMA producer: Q once; then the ring in consumption order K(0), [K(j+1), V(j)]... ----------------
+            mbar_expect_tx(q_full, NCH * SM::CHUNK);
+            for (int c = 0; c < NCH; ++c) tma_load_2d(sQ + c * SM::CHUNK, &tmQ, q_full, c * 64, batch * p.L + q0);
+            int slot = 0;
+            uint32_t phase = 0;
+            auto push = [&](const CUtensorMap* tm, int col, int row) {
+                mbar_wait(&slot_empty[slot], phase ^ 1);
+                mbar_expect_tx(&slot_full[slot], SM::CHUNK);
+                tma_load_2d(ring + slot * SM::CHUNK, tm, &slot_full[slot], col, row);
+                if (++slot == A5_SLOTS) { slot = 0; phase ^= 1; }
+            };
+            for (int c = 0; c < NCH; ++c) push(&tmK, c * 64, batch * p.L);
+            for (int j = 0; j < nblk; ++j) {
+                if (j + 1 < nblk)
+                    for (int c = 0; c < NCH; ++c) push(&tmK, c * 64, batch * p.L + (j + 1) * ATT_BN);
+                for (int d = 0; d < NVC; ++d) push(&tmV, half * A5_DV + d * 64, batch * p.L + j * ATT_BN);
+            }
+        }
+      } else if (warp == 1) {
+        if (lane == 0) {
+            // ---------------- MMA issuer ----------------
+            const uint64_t dtemplate = (uint64_t)p.desc_hi << 32;
+            int slot = 0;
+            uint32_t phase = 0;
+            auto next_slot = [&]() { if (++slot == A5_SLOTS) { slot = 0; phase ^= 1; } };
+            auto issue_qk = [&](int buf) {
+                for (int c = 0; c < NCH; ++c) {
+                    mbar_wait(&slot_full[slot], phase);
+                    tc_fence_after();
+                    const uint64_t qdesc = dtemplate | ((smem_u32(sQ + c * SM::CHUNK) >> 4) & 0x3FFF);
+                    const uint64_t kdesc = dtemplate | ((smem_u32(ring + slot * SM::CHUNK) >> 4) & 0x3FFF);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_bf16(tmem_base + COL_S + buf * ATT_BN, qdesc + 2 * kk, kdesc + 2 * kk, p.idesc_qk, (c | kk) != 0);
+                    umma_commit(&slot_empty[slot]);
+                    next_slot();
+                }
+                umma_commit(&s_full[buf]);
+            };
+            mbar_wait(q_full, 0);
+            issue_qk(0);
+            for (int j = 0; j < nblk; ++j) {
+                const int buf = j & 1;
+                if (j + 1 < nblk) issue_qk(buf ^ 1);              // S[buf^1] is free: PV(j-1), which read P there, was issued before
+                mbar_wait(&p_full[buf], (j >> 1) & 1);            // P(j) written over S[buf]
+                tc_fence_after();
+                for (int d = 0; d < NVC; ++d) {
+                    mbar_wait(&slot_full[slot], phase);
+                    tc_fence_after();
+                    const uint32_t vbase = smem_u32(ring + slot * SM::CHUNK);
+#pragma unroll
+                    for (int kk = 0; kk < ATT_BN / 16; ++kk) {
+                        const uint32_t va = vbase + kk * 16 * 128;
+                        umma_bf16_ts(tmem_base + d * 64, tmem_base + COL_S + buf * ATT_BN + kk * 8, dtemplate | ((va >> 4) & 0x3FFF),
+                                     p.idesc_pv, (j | kk) != 0);
+                    }
+                    umma_commit(&slot_empty[slot]);
+                    next_slot();
+                }
+                umma_commit(pv_done);
+            }
+        }
+      }
+    } else {
+        // ---------------- softmax / output warps (warps 4..7) ----------------
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+        const uint32_t tO = tmem_base + lane_off;
+        float m_ref = 0.f, l_run = 0.f;
+        for (int j = 0; j < nblk; ++j) {
+            const int buf = j & 1;
+            const uint32_t tS = tmem_base + COL_S + buf * ATT_BN + lane_off;
+            mbar_wait(&s_full[buf], (j >> 1) & 1);
+            tc_fence_after();
+            uint32_t s[128];
+            tmem_ld_32x32_at<0>(tS + 0, s);
+            tmem_ld_32x32_at<32>(tS + 32, s);
+            tmem_ld_32x32_at<64>(tS + 64, s);
+            tmem_ld_32x32_at<96>(tS + 96, s);
+            tmem_ld_wait();
+            const int kv_valid = min(ATT_BN, p.L - j * ATT_BN);
+            if (kv_valid < ATT_BN) {
+#pragma unroll
+                for (int i = 0; i < ATT_BN; ++i)
+                    if (i >= kv_valid) s[i] = 0xff800000u;
+            }
+            float mxa[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) mxa[t] = __uint_as_float(s[t]);
+#pragma unroll
+            for (int i = 8; i < ATT_BN; i += 8) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) mxa[t] = fmaxf(mxa[t], __uint_as_float(s[i + t]));
+            }
+            float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])), fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
+            mx *= p.scale_log2;
+            if (j == 0) {
+                m_ref = mx;
+            } else {
+                const bool need = mx > m_ref + ATT_RESCALE_THRESHOLD;
+                if (__any_sync(0xffffffffu, need)) {
+                    mbar_wait(pv_done, (j - 1) & 1);               // PV(j-1) is the last writer of O
+                    tc_fence_after();
+                    const float alpha = need ? ex2_approx(m_ref - mx) : 1.0f;
+                    if (need) m_ref = mx;
+                    l_run *= alpha;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < A5_DV; c0 += 32) {
+                        uint32_t o[32];
+                        tmem_ld_32x32(tO + c0, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st_32x32(tO + c0, o);
+                    }
+                    tmem_st_wait();
+                }
+            }
+            // P(j) overwrites the first 64 columns of S[buf]: its previous reader, PV(j-2), retired before QK(j) could run
+            l_run += softmax_row_to_tmem<ATT_BN, EMU>(s, p.scale_log2, m_ref, tS);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[buf]);
+        }
+        mbar_wait(pv_done, (nblk - 1) & 1);
+        tc_fence_after();
+        const int qrow = q0 + row;
+        const float inv = 1.f / l_run;
+        __nv_bfloat16* dst = p.out + ((long long)batch * p.L + qrow) * p.ldo + half * A5_DV;
+#pragma unroll 1
+        for (int c0 = 0; c0 < A5_DV; c0 += 32) {
+            uint32_t o[32];
+            tmem_ld_32x32(tO + c0, o);
+            tmem_ld_wait();
+            if (qrow < p.L) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint4 u;
+                    u.x = pack_bf16x2(__uint_as_float(o[q * 8 + 0]) * inv, __uint_as_float(o[q * 8 + 1]) * inv);
+                    u.y = pack_bf16x2(__uint_as_float(o[q * 8 + 2]) * inv, __uint_as_float(o[q * 8 + 3]) * inv);
+                    u.z = pack_bf16x2(__uint_as_float(o[q * 8 + 4]) * inv, __uint_as_float(o[q * 8 + 5]) * inv);
+                    u.w = pack_bf16x2(__uint_as_float(o[q * 8 + 6]) * inv, __uint_as_float(o[q * 8 + 7]) * inv);
+                    reinterpret_cast<uint4*>(dst + c0)[q] = u;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+template <int D, int EMU>
+static int launch_attention_d512(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const Attn512Params& p,
+                                 int B, cudaStream_t st) {
+    using SM = Attn512Smem<D>;
+    static bool attr_set[64] = {};
+    int dev = 0;
+    SUPIR_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        SUPIR_CHECK_CUDA(cudaFuncSetAttribute(attention_d512_kernel<D, EMU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    dim3 grid((p.L + ATT_BM - 1) / ATT_BM, D / SM::DV, B);
+    attention_d512_kernel<D, EMU><<<grid, 256, SM::TOTAL, st>>>(tmQ, tmK, tmV, p);
+    count_launch();
+    SUPIR_CHECK_CUDA(cudaGetLastError());
+    return SUPIR_OK;
+}
+
+}  // namespace supir
+
+extern "C" int supir_attention_1head_bf16(const void* q, long long ldq, const void* k, long long ldk, const void* v,
+                                          long long ldv, void* out, long long ldo, int B, int L, int head_dim, float scale,
+                                          void* stream) {
+    SUPIR_REQUIRE(q && k && v && out, "supir_attention_1head_bf16: null pointer");
+    SUPIR_REQUIRE(B > 0 && L > 0 && scale > 0.f, "supir_attention_1head_bf16: bad shape");
+    SUPIR_REQUIRE(head_dim == 512 || head_dim == 256 || head_dim == 128, "supir_attention_1head_bf16: head_dim %d not in {128, 256, 512}", head_dim);
+    SUPIR_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && ldq >= head_dim && ldk >= head_dim && ldv >= head_dim && ldo >= head_dim,
+                  "supir_attention_1head_bf16: leading dims must be multiples of 8 and >= head_dim");
+    CUtensorMap tmQ, tmK, tmV;
+    int rc;
+    const uint32_t box[2] = {64, ATT_BM};
+    const uint64_t dims[2] = {(uint64_t)head_dim, (uint64_t)B * L};
+    const uint64_t sq[1] = {(uint64_t)ldq}, sk[1] = {(uint64_t)ldk}, sv[1] = {(uint64_t)ldv};
+    if ((rc = make_tmap_bf16(&tmQ, q, 2, dims, sq, box))) return rc;
+    if ((rc = make_tmap_bf16(&tmK, k, 2, dims, sk, box))) return rc;
+    if ((rc = make_tmap_bf16(&tmV, v, 2, dims, sv, box))) return rc;
+    Attn512Params p{};
+    p.L = L;
+    p.ldo = ldo;
+    p.out = reinterpret_cast<__nv_bfloat16*>(out);
+    p.scale_log2 = scale * 1.4426950408889634f;
+    const uint64_t dt = g_att_desc_override >= 0 ? (uint64_t)g_att_desc_override
+                                                 : (((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61));
+    p.desc_hi = (uint32_t)(dt >> 32);
+    p.idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN, 0, 0);
+    p.idesc_pv = umma_idesc_bf16(ATT_BM, 64, 0, 1);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int emu = attention_emu();
+    if (head_dim == 512) {
+        if (emu == 0) return launch_attention_d512<512, 0>(tmQ, tmK, tmV, p, B, st);
+        if (emu == 4) return launch_attention_d512<512, 4>(tmQ, tmK, tmV, p, B, st);
+        return launch_attention_d512<512, 2>(tmQ, tmK, tmV, p, B, st);
+    }
+    if (head_dim == 256) return launch_attention_d512<256, 2>(tmQ, tmK, tmV, p, B, st);
+    return launch_attention_d512<128, 2>(tmQ, tmK, tmV, p, B, st);
 }

@@ -351,6 +351,72 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// packed fp32 pairs (sm_100 FFMA2 / FADD2: two fp32 operations per issue slot)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t fadd2_rm(uint64_t a, uint64_t b) {   // round towards -inf
+    uint64_t d;
+    asm("add.rm.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// both halves rounded to bf16 and widened back to fp32 (the value a bf16 tensor would hold)
+__device__ __forceinline__ uint64_t bf16_round2(uint64_t v) {
+    float lo, hi;
+    unpack2(v, lo, hi);
+    const uint32_t pk = pack_bf16x2(lo, hi);
+    return pack2(__uint_as_float(pk << 16), __uint_as_float(pk & 0xffff0000u));
+}
+// erf-form GELU of two values (same formulation and constants as gelu_erf_f): the polynomial and the products run as packed
+// FFMA2 / FMUL2, the two MUFU operations (rcp, ex2) per element stay scalar
+__device__ __forceinline__ uint64_t gelu_erf_f2(uint64_t g) {
+    float g0, g1;
+    unpack2(g, g0, g1);
+    const uint64_t ag = pack2(fabsf(g0), fabsf(g1));
+    float d0, d1;
+    unpack2(ffma2(pack2(0.2316418882f, 0.2316418882f), ag, pack2(1.0f, 1.0f)), d0, d1);
+    float t0, t1;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+    const uint64_t t = pack2(t0, t1);
+    uint64_t poly = ffma2(pack2(1.061405429f, 1.061405429f), t, pack2(-1.453152027f, -1.453152027f));
+    poly = ffma2(poly, t, pack2(1.421413741f, 1.421413741f));
+    poly = ffma2(poly, t, pack2(-0.284496736f, -0.284496736f));
+    poly = ffma2(poly, t, pack2(0.254829592f, 0.254829592f));
+    poly = fmul2(poly, t);
+    float x0, x1;
+    unpack2(fmul2(fmul2(g, g), pack2(-0.7213475204f, -0.7213475204f)), x0, x1);
+    const uint64_t e = pack2(ex2_approx(x0), ex2_approx(x1));
+    float p0, p1;
+    unpack2(poly, p0, p1);
+    const uint64_t erf_abs = ffma2(pack2(-p0, -p1), e, pack2(1.0f, 1.0f));
+    const uint64_t h = fmul2(g, pack2(0.5f, 0.5f));
+    return ffma2(fmul2(ag, pack2(0.5f, 0.5f)), erf_abs, h);
+}
+
+// ---------------------------------------------------------------------------------------------
 // UMMA descriptors (layout documented in DESIGN.md §kernels; bit positions follow the PTX ISA
 // "tcgen05 shared memory descriptor" / "instruction descriptor" tables)
 // ---------------------------------------------------------------------------------------------

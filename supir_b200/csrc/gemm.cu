@@ -308,17 +308,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const float* cc = sc + c * 32;
                 uint4 q[4];
                 if (geglu) {
-                    float o[16], bb[32];
+                    // packed fp32 pairs (FADD2 / FFMA2 / FMUL2): two outputs per issue slot outside the MUFU operations
+                    uint32_t o[8];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(&bb[j]) = *reinterpret_cast<const float4*>(bc + j);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float xv = bf16_round(__uint_as_float(r[j]) + bb[j]);
-                        const float gv = bf16_round(__uint_as_float(r[16 + j]) + bb[16 + j]);
-                        o[j] = xv * bf16_round(gelu_erf_f(gv));
+                    for (int j = 0; j < 16; j += 2) {
+                        const float2 bx = *reinterpret_cast<const float2*>(bc + j);
+                        const float2 bg = *reinterpret_cast<const float2*>(bc + 16 + j);
+                        const uint64_t xv = bf16_round2(fadd2(pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), pack2(bx.x, bx.y)));
+                        const uint64_t gv = bf16_round2(fadd2(pack2(__uint_as_float(r[16 + j]), __uint_as_float(r[17 + j])), pack2(bg.x, bg.y)));
+                        float o0, o1;
+                        unpack2(fmul2(xv, bf16_round2(gelu_erf_f2(gv))), o0, o1);
+                        o[j >> 1] = pack_bf16x2(o0, o1);
                     }
-                    q[0] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-                    q[1] = make_uint4(pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]), pack_bf16x2(o[12], o[13]), pack_bf16x2(o[14], o[15]));
+                    q[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                    q[1] = make_uint4(o[4], o[5], o[6], o[7]);
                 } else {
                     float v[32];
                     if (p.ln_stats) {

@@ -119,6 +119,19 @@ def attention(q, k, v, out, B, heads, Lq, Lk, scale=None):
     return out
 
 
+def attention_1head(q, k, v, out, B, L, scale=None):
+    """One wide head (head_dim = columns: 512 for the SDXL VAE, 128 / 256 for reduced configs) over L tokens per batch
+    element (VAE mid-block attention); q/k/v/out [B*L, head_dim] bf16 (row stride = leading dimension)."""
+    _need_cuda(q, k, v, out)
+    D = q.shape[1]
+    for t in (q, k, v, out):
+        _mat(t)
+        assert t.shape == (B * L, D), t.shape
+    call("supir_attention_1head_bf16", _ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out), out.stride(0),
+         B, L, D, float(scale if scale is not None else D ** -0.5), _stream())
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # normalisation
 # ------------------------------------------------------------------------------------------------------------------

@@ -117,10 +117,9 @@ class _VAENet(nn.Module):
             C = a.in_channels
             add(("store_res", None, None, C))
             add(norm(a.norm))
-            wqk = _bf(torch.cat([a.q.weight.reshape(C, C), a.k.weight.reshape(C, C)], 0))
-            bqk = torch.cat([_bias_bf16_values(a.q.bias), _bias_bf16_values(a.k.bias)], 0).contiguous()
-            add(("attn", wqk, bqk, _bf(a.v.weight.reshape(C, C)), _bias_bf16_values(a.v.bias),
-                 _bf(a.proj_out.weight.reshape(C, C)), _bias_bf16_values(a.proj_out.bias), C))
+            wqkv = _bf(torch.cat([a.q.weight.reshape(C, C), a.k.weight.reshape(C, C), a.v.weight.reshape(C, C)], 0))
+            bqkv = torch.cat([_bias_bf16_values(a.q.bias), _bias_bf16_values(a.k.bias), _bias_bf16_values(a.v.bias)], 0).contiguous()
+            add(("attn", wqkv, bqkv, _bf(a.proj_out.weight.reshape(C, C)), _bias_bf16_values(a.proj_out.bias), C))
             add(("add_res",))
 
         ci = self.conv_in
@@ -198,31 +197,19 @@ class _VAENet(nn.Module):
             raise ValueError(kind)
 
     def _attn(self, pool, step, tile, add_res=False):
-        """softmax(q k^T c^-0.5) v with one 512-wide head: two tensor-core GEMMs around a row-softmax kernel; the score
-        matrix is materialised in HBM (fp32) — memory is not the constraint on a 180 GB part, and it is < 2 % of the VAE."""
-        _, wqk, bqk, wv, bv, wo, bo, C = step
+        """softmax(q k^T c^-0.5) v with one 512-wide head (model.py:187-189, tilevae.py:292-336): fused Q|K|V projection, the
+        flash-style head_dim-512 kernel (no score matrix in HBM), output projection with the block's skip in its epilogue."""
+        _, wqkv, bqkv, wo, bo, C = step
         a: Act = tile["h"]
         L = a.HW
-        Lp = (L + 7) // 8 * 8
-        out = pool.get((a.rows, C))
         r = tile["res"].pop() if add_res else None
-        for b in range(a.B):
-            x = a.t[b * L:(b + 1) * L]
-            qk = pool.get((L, 2 * C))
-            ops.gemm(x, wqk, qk, bias=bqk)
-            # v^T [C, L] = Wv x^T (+ bias per row): swapped-operand GEMM gives the K-major B operand of P @ V directly
-            vT = pool.get((C, Lp))
-            ops.gemm(wv, x, vT[:, :L], rowvec=None)
-            S = pool.get((L, Lp), torch.float32)
-            ops.gemm(qk[:, :C], qk[:, C:], S[:, :L])
-            P = pool.get((L, Lp))
-            ops.softmax_rows(S, P, L, float(int(C) ** (-0.5)))
-            o = pool.get((L, C))
-            # softmax rows sum to one, so the value bias can be added after the product: (P (V + 1 b^T)) = P V + 1 b^T
-            ops.gemm(P[:, :L], vT[:, :L], o, bias=bv)
-            ops.gemm(o, wo, out[b * L:(b + 1) * L], bias=bo, residual=None if r is None else r[b * L:(b + 1) * L])
-            pool.put(qk, vT, S, P, o)
-        pool.put(a.t, r)
+        qkv = pool.get((a.rows, 3 * C))
+        ops.gemm(a.t, wqkv, qkv, bias=bqkv)
+        o = pool.get((a.rows, C))
+        ops.attention_1head(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, a.B, L, float(int(C) ** (-0.5)))
+        out = pool.get((a.rows, C))
+        ops.gemm(o, wo, out, bias=bo, residual=r)
+        pool.put(qkv, o, a.t, r)
         tile["h"] = Act(out, a.B, a.H, a.W)
 
     def _norm_apply(self, pool, step, tile, sums=None, mean=None, var=None):

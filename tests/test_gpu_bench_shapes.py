@@ -255,3 +255,26 @@ def test_attention_adversarial_logits_force_rescale(Lk, emu):
         _check_attention(out, ref_d, f"descending-logit attention Lk={Lk} emu={emu}")
     finally:
         lib.supir_set_attention_exp_emulation(-1)
+
+
+@pytest.mark.parametrize("B,L,D", [(1, 18496, 512), (1, 22500, 512), (2, 300, 512), (1, 128, 512), (2, 777, 256), (3, 200, 128), (1, 4096, 128)])
+def test_vae_single_head_attention(B, L, D):
+    """The VAE mid-block attention (model.py:187-189; tilevae.py:292-336) at the token counts of the bench's padded tiles
+    (136^2 = 18 496 for a 1088-px encoder tile, 150^2 = 22 500 for a 150-latent decoder tile) and ragged small cases."""
+    ops, native = _ops()
+    q, k, v = _rand((B * L, D), 51, 1.0), _rand((B * L, D), 52, 1.0), _rand((B * L, D), 53)
+    scale = D ** -0.5
+    ref = torch.empty((B * L, D), dtype=torch.float32, device="cuda")
+    for b in range(B):
+        sl = slice(b * L, (b + 1) * L)
+        for r0 in range(0, L, 4096):
+            p = torch.softmax(q[sl][r0:r0 + 4096].float() @ k[sl].float().t() * scale, dim=-1)
+            ref[b * L + r0:b * L + min(r0 + 4096, L)] = p @ v[sl].float()
+    out = torch.full((B * L, D), float("nan"), dtype=BF, device="cuda")
+    ops.attention_1head(q, k, v, out, B, L)
+    _check_attention(out, ref, f"single-head attention B={B} L={L} D={D}")
+    # operands as column slices of a fused [L, 3D] projection (how the VAE calls it)
+    qkv = torch.cat([q, k, v], 1).contiguous()
+    out2 = torch.full((B * L, D), float("nan"), dtype=BF, device="cuda")
+    ops.attention_1head(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], out2, B, L)
+    assert torch.equal(out, out2)

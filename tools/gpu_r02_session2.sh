@@ -13,6 +13,7 @@ run 90 r02_selftest_attnquick.log tools/selftest attnquick || { tail -n 30 gpuru
 tail -n 8 gpurun_out/r02_selftest_attnquick.log
 run 240 r02_selftest_attn.log tools/selftest attn; tail -n 12 gpurun_out/r02_selftest_attn.log
 run 240 r02_selftest_attnperf2.log tools/selftest attnperf2; cat gpurun_out/r02_selftest_attnperf2.log
+run 240 r02_selftest_epiperf.log tools/selftest epiperf; cat gpurun_out/r02_selftest_epiperf.log
 run 600 r02_pytest_bench_shapes.log python -m pytest tests/test_gpu_bench_shapes.py -x -q -m gpu -s; tail -n 25 gpurun_out/r02_pytest_bench_shapes.log
 run 900 r02_pytest_gpu_rest.log python -m pytest tests -x -q -m gpu --ignore=tests/test_gpu_bench_shapes.py -s --durations=15; tail -n 45 gpurun_out/r02_pytest_gpu_rest.log
 run 420 r02_bench_s2.log python bench.py --steps 5 --warmup 3 --no-cpu-baseline; tail -n 3 gpurun_out/r02_bench_s2.log

@@ -282,6 +282,64 @@ static void perf_gemm(int M, int N, int K, int act, int bn) {
     fflush(stdout);
 }
 
+// pseudo-random bf16 fill (hash of the index, roughly uniform in [-amp, amp]): realistic operand toggling for power / timing
+__global__ void fill_random_bf16(__nv_bfloat16* p, size_t n, float amp, uint32_t seed) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t h = (uint32_t)i * 2654435761u ^ seed;
+        h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+        p[i] = __float2bfloat16_rn(((h >> 8) * (1.0f / 8388608.0f) - 1.0f) * amp);
+    }
+}
+
+// step-realistic GEMM timing: random operands (power draw), bias (+ residual), 30 back-to-back launches
+static void perf_gemm_real(int M, int N, int K, int act, bool with_res, bool with_ln = false) {
+    const int n_out = act == 2 ? N / 2 : N;
+    __nv_bfloat16 *dA, *dW, *dOut, *dRes = nullptr;
+    float *dBias, *dStats = nullptr, *dC1 = nullptr;
+    CK(cudaMalloc(&dA, (size_t)M * K * 2));
+    CK(cudaMalloc(&dW, (size_t)N * K * 2));
+    CK(cudaMalloc(&dOut, (size_t)M * n_out * 2));
+    CK(cudaMalloc(&dBias, (size_t)N * 4));
+    CK(cudaMemset(dBias, 0, (size_t)N * 4));
+    fill_random_bf16<<<1024, 256>>>(dA, (size_t)M * K, 1.0f, 11u);
+    fill_random_bf16<<<1024, 256>>>(dW, (size_t)N * K, 0.05f, 12u);
+    supir_epilogue ep{};
+    ep.act = act;
+    ep.bias = dBias;
+    if (with_res) {
+        CK(cudaMalloc(&dRes, (size_t)M * n_out * 2));
+        fill_random_bf16<<<1024, 256>>>(dRes, (size_t)M * n_out, 1.0f, 13u);
+        ep.residual = dRes;
+        ep.ldr = n_out;
+    }
+    if (with_ln) {
+        CK(cudaMalloc(&dStats, (size_t)M * 8));
+        CK(cudaMalloc(&dC1, (size_t)N * 4));
+        CK(cudaMemset(dC1, 0, (size_t)N * 4));
+        supir_layernorm_stats(dA, K, M, K, 1e-5f, dStats, nullptr);
+        ep.ln_stats = dStats;
+        ep.ln_colsum = dC1;
+    }
+    for (int i = 0; i < 3; ++i) supir_gemm_bf16(dA, K, dW, K, dOut, n_out, M, N, K, &ep, nullptr);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int iters = 30;
+    cudaEventRecord(e0);
+    for (int i = 0; i < iters; ++i) supir_gemm_bf16(dA, K, dW, K, dOut, n_out, M, N, K, &ep, nullptr);
+    cudaEventRecord(e1);
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ms /= iters;
+    printf("[PERF] gemm M=%d N=%d K=%d act=%d res=%d ln=%d : %.3f ms  %.1f TFLOP/s\n", M, N, K, act, (int)with_res, (int)with_ln, ms,
+           2.0 * M * N * K / ms / 1e9);
+    cudaFree(dA); cudaFree(dW); cudaFree(dOut); cudaFree(dBias);
+    if (dRes) cudaFree(dRes);
+    if (dStats) cudaFree(dStats);
+    if (dC1) cudaFree(dC1);
+    fflush(stdout);
+}
+
 static void perf_conv(int B, int H, int Wd, int Cin, int Cout, int bn) {
     __nv_bfloat16 *dX, *dW, *dOut;
     CK(cudaMalloc(&dX, (size_t)B * H * Wd * Cin * 2));
@@ -375,15 +433,6 @@ static bool test_attention(int B, int H, int Lq, int Lk, int sample_rows) {
     bool ok = report(name, max_err, max_ref, 0.02, bad);
     cudaFree(dQ); cudaFree(dK); cudaFree(dV); cudaFree(dO);
     return ok;
-}
-
-// pseudo-random bf16 fill (hash of the index, roughly uniform in [-amp, amp]): realistic operand toggling for power / timing
-__global__ void fill_random_bf16(__nv_bfloat16* p, size_t n, float amp, uint32_t seed) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        uint32_t h = (uint32_t)i * 2654435761u ^ seed;
-        h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
-        p[i] = __float2bfloat16_rn(((h >> 8) * (1.0f / 8388608.0f) - 1.0f) * amp);
-    }
 }
 
 static void perf_attention(int B, int H, int Lq, int Lk) {
@@ -565,6 +614,23 @@ int main(int argc, char** argv) {
             perf_conv(14, 64, 64, 640, 640, 256);
         }
         supir_set_gemm_pair_mode(1);
+    }
+    if (what == "epiperf") {     // the step's dominant GEMM shapes (batch 98) under both staged-epilogue modes
+        for (int mode : {0, 1}) {
+            printf("-- staged epilogue mode %d (%s)\n", mode, mode ? "per-warp TMA, no named barriers" : "one TMA op per 128-row chunk");
+            supir_set_gemm_epilogue_mode(mode);
+            perf_gemm_real(100352, 10240, 1280, 2, false);
+            perf_gemm_real(100352, 1280, 5120, 0, true);
+            perf_gemm_real(100352, 1280, 1280, 0, true);
+            perf_gemm_real(100352, 3840, 1280, 0, false);
+            perf_gemm_real(100352, 3840, 1280, 0, false, true);
+            perf_gemm_real(401408, 5120, 640, 2, false);
+            perf_gemm_real(401408, 640, 640, 0, true);
+            perf_gemm_real(401408, 640, 2560, 0, true);
+            perf_gemm_real(401408, 1920, 640, 0, false);
+            perf_gemm_real(401408, 1920, 640, 0, false, true);
+        }
+        supir_set_gemm_epilogue_mode(-1);
     }
     if (what == "attnquick") {     // hang guard for a GPU session: every kernel variant once, small
         for (int emu : {2, 0, 4}) {
