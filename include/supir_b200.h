@@ -59,6 +59,25 @@ int supir_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, 
 int supir_conv3x3_bf16(const void* x, long long ldx, const void* Wp, void* out, long long ldc, int B, int H, int W,
                        int Cin, int Cout, const supir_epilogue* ep, void* stream);
 
+/* General small-kernel convolution on NHWC bf16 through the same implicit-GEMM kernel (no im2col buffer): kh x kw taps
+ * (1..3 each), stride 1 or 2 (TMA element strides gather every second input pixel), arbitrary tap offset = padding, and an
+ * optional interleaved output placement. Input pixel of tap (ky, kx) for output (y, x):
+ *   (y * stride + ky + off_y, x * stride + kx + off_x), zero outside the image.
+ * Output pixel (y, x) of the Hout x Wout grid is written to (y * out_sy + out_oy, x * out_sx + out_ox) of out
+ * [B, out_H, out_W, ldc]. Wp: [Cout, kh, kw, Cin]. Uses:
+ *   - Downsample, 3x3 stride 2 pad 1 (openaimodel.py:196-210): off -1, Hout = (Hin - 1) / 2 + 1;
+ *   - VAE Downsample, pad (0,1,0,1) then 3x3 stride 2 (model.py:81-85): off 0, Hout = (Hin - 2) / 2 + 1;
+ *   - Upsample, nearest 2x then 3x3 pad 1 (openaimodel.py:131-151, model.py:64-68) as FOUR 2x2 convolutions on the
+ *     low-resolution input, one per output parity (py, px), with the 3x3 weights pre-summed per parity
+ *     (2.25x fewer FLOPs, no 4x intermediate): kh = kw = 2, off = (py - 1, px - 1), out_s = 2, out_o = (py, px). */
+typedef struct supir_conv_geometry {
+    int kh, kw, stride, off_y, off_x;
+    int Hout, Wout;
+    int out_sy, out_sx, out_oy, out_ox, out_H, out_W;
+} supir_conv_geometry;
+int supir_conv_geom_bf16(const void* x, long long ldx, const void* Wp, void* out, long long ldc, int B, int Hin, int Win, int Cin,
+                         int Cout, const supir_conv_geometry* geom, const supir_epilogue* ep, void* stream);
+
 /* debugging / tuning knob: force the N tile (64/128/256), 0 = heuristic */
 int supir_set_gemm_tile_n(int bn);
 /* tuning knob: the widest tile can run on CTA pairs (2-CTA clusters, tcgen05 cta_group::2: a 256 x 256 tile per pair,

@@ -17,10 +17,18 @@ class Epilogue(ctypes.Structure):
                 ("residual", c_void_p), ("ldr", c_ll), ("act", c_int), ("out_f32", c_int), ("ln_stats", c_void_p), ("ln_colsum", c_void_p)]
 
 
+class ConvGeometry(ctypes.Structure):
+    """struct supir_conv_geometry (include/supir_b200.h)."""
+    _fields_ = [(n, c_int) for n in ("kh", "kw", "stride", "off_y", "off_x", "Hout", "Wout", "out_sy", "out_sx", "out_oy", "out_ox",
+                                     "out_H", "out_W")]
+
+
 # name -> argtypes (all return int unless listed in _SPECIAL)
 _SIGS = {
     "supir_gemm_bf16": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, ctypes.POINTER(Epilogue), c_void_p],
     "supir_conv3x3_bf16": [c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(Epilogue), c_void_p],
+    "supir_conv_geom_bf16": [c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(ConvGeometry),
+                             ctypes.POINTER(Epilogue), c_void_p],
     "supir_set_gemm_tile_n": [c_int],
     "supir_set_gemm_pair_mode": [c_int],
     "supir_set_gemm_epilogue_mode": [c_int],

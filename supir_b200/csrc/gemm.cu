@@ -40,7 +40,12 @@ struct GemmKernelParams {
     int m_fastest;        // tile order: 1 = consecutive tiles share the W tile, 0 = they share the A tile
     // conv mode
     int conv;             // 0 gemm, 1 conv3x3
-    int H, W, Cin, TH, TW, tiles_x, tiles_y, kchunks;
+    int H, W, Cin, TH, TW, tiles_x, tiles_y, kchunks;   // H, W: OUTPUT grid of the convolution
+    // conv geometry (supir_conv_geometry): taps kh x ntaps_x, input pixel of tap (ky, kx) for output (y, x) =
+    // (y * stride + ky + off_y, x * stride + kx + off_x); out-of-image taps read TMA's zero fill
+    int ntaps_x, stride, off_y, off_x;
+    // where output pixel (y, x) lands in the output tensor [nimg, out_H, out_W, ldc]: (y * out_sy + out_oy, x * out_sx + out_ox)
+    int out_sy, out_sx, out_oy, out_ox, out_H, out_W;
     // epilogue
     const float* bias;
     const float* rowvec;
@@ -163,12 +168,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (p.conv) {
                         const int tap = kb / p.kchunks;
                         const int cc = kb - tap * p.kchunks;
-                        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                        const int dy = tap / p.ntaps_x + p.off_y, dx = tap % p.ntaps_x + p.off_x;
+                        const int ax = x0 * p.stride + dx, ay = y0 * p.stride + dy;
                         if (CTAS == 2) {
-                            tma_load_4d_2sm(sa, &tmA, &full_bar[stage], cc * BK, x0 + dx, y0 + dy, b);
+                            tma_load_4d_2sm(sa, &tmA, &full_bar[stage], cc * BK, ax, ay, b);
                             tma_load_2d_2sm(sb, &tmB, &full_bar[stage], tap * p.Cin + cc * BK, bn0);
                         } else {
-                            tma_load_4d(sa, &tmA, &full_bar[stage], cc * BK, x0 + dx, y0 + dy, b);
+                            tma_load_4d(sa, &tmA, &full_bar[stage], cc * BK, ax, ay, b);
                             tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.Cin + cc * BK, bn0);
                         }
                     } else {
@@ -428,7 +434,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int y = (r / p.tiles_x) * p.TH + row_in_tile / p.TW;
                 const int x = (r % p.tiles_x) * p.TW + row_in_tile % p.TW;
                 row_ok = (y < p.H) && (x < p.W) && (b < p.nimg);
-                grow = ((long long)b * p.H + y) * p.W + x;
+                grow = ((long long)b * p.out_H + (long long)y * p.out_sy + p.out_oy) * p.out_W + (long long)x * p.out_sx + p.out_ox;
                 batch_idx = b;
             } else {
                 grow = (long long)rt * BM + row_in_tile;
@@ -638,6 +644,25 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* d
     return make_tmap_bf16_sw(m, base, rank, dims, strides_elems, box, 128);
 }
 
+// same with traversal strides (elementStrides): the box spans box[i] tensor elements of dimension i and delivers every
+// elem_strides[i]-th of them, densely packed (a stride-2 convolution's input patch)
+int make_tmap_bf16_strided(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                           const uint32_t* box, const uint32_t* elem_strides) {
+    PFN_tmapEncodeTiled fn = get_encode_fn();
+    if (!fn) return set_error(SUPIR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = elem_strides[i]; }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_elems[i] * 2;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(SUPIR_ERR_INVALID, "TMA base address %p is not 16-byte aligned", base);
+    for (int i = 0; i + 1 < rank; ++i)
+        if (gstr[i] % 16 != 0) return set_error(SUPIR_ERR_INVALID, "TMA stride %d (%llu B) not a multiple of 16", i, (unsigned long long)gstr[i]);
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(SUPIR_ERR_CUDA, "cuTensorMapEncodeTiled (strided) failed with CUresult %d", (int)r);
+    return SUPIR_OK;
+}
+
 int device_sm_count() {
     static int sms = 0;
     if (sms == 0) {
@@ -774,6 +799,7 @@ static int gemm_epilogue_mode() {
 // staged epilogue applies to bf16 outputs with 16-byte aligned rows; it needs the per-image vector to be uniform per tile
 static bool can_stage(const GemmKernelParams& p) {
     if (g_force_direct_epilogue || p.out_f32) return false;
+    if (p.conv && (p.out_sy != 1 || p.out_sx != 1)) return false;     // interleaved (sub-pixel) outputs: per-row addresses
     if ((p.ldc & 7) || (reinterpret_cast<uintptr_t>(p.out) & 15)) return false;
     if (p.n_out < (p.act == 2 ? 16 : 32)) return false;
     if (p.rowvec && !p.conv) return false;
@@ -924,14 +950,21 @@ extern "C" int supir_gemm_bf16(const void* A, long long lda, const void* W, long
     return run_gemm(tmA, tmB, p, reinterpret_cast<cudaStream_t>(stream));
 }
 
-extern "C" int supir_conv3x3_bf16(const void* x, long long ldx, const void* Wp, void* out, long long ldc, int B, int H,
-                                  int Wd, int Cin, int Cout, const supir_epilogue* ep, void* stream) {
-    SUPIR_REQUIRE(x && Wp && out, "supir_conv3x3_bf16: null pointer");
-    SUPIR_REQUIRE(B > 0 && H > 0 && Wd > 0 && Cin > 0 && Cout > 0, "supir_conv3x3_bf16: bad shape");
-    SUPIR_REQUIRE(Cin % 8 == 0 && ldx % 8 == 0 && ldx >= Cin, "supir_conv3x3_bf16: Cin/ldx must be multiples of 8");
+static int conv_geom_impl(const char* who, const void* x, long long ldx, const void* Wp, void* out, long long ldc, int B, int Hin, int Win,
+                          int Cin, int Cout, const supir_conv_geometry& g, const supir_epilogue* ep, void* stream) {
+    SUPIR_REQUIRE(x && Wp && out, "%s: null pointer", who);
+    SUPIR_REQUIRE(B > 0 && Hin > 0 && Win > 0 && Cin > 0 && Cout > 0, "%s: bad shape", who);
+    SUPIR_REQUIRE(Cin % 8 == 0 && ldx % 8 == 0 && ldx >= Cin, "%s: Cin/ldx must be multiples of 8", who);
+    SUPIR_REQUIRE(g.kh >= 1 && g.kh <= 3 && g.kw >= 1 && g.kw <= 3 && (g.stride == 1 || g.stride == 2), "%s: kernel %dx%d stride %d unsupported", who, g.kh, g.kw, g.stride);
+    SUPIR_REQUIRE(g.Hout > 0 && g.Wout > 0 && g.out_sy >= 1 && g.out_sx >= 1 && g.out_oy >= 0 && g.out_ox >= 0 && g.out_oy < g.out_sy &&
+                  g.out_ox < g.out_sx && g.out_H >= (g.Hout - 1) * g.out_sy + g.out_oy + 1 && g.out_W >= (g.Wout - 1) * g.out_sx + g.out_ox + 1,
+                  "%s: bad output geometry", who);
+    const int H = g.Hout, Wd = g.Wout, ntaps = g.kh * g.kw;
     GemmKernelParams p{};
     p.conv = 1;
     p.H = H; p.W = Wd; p.Cin = Cin;
+    p.ntaps_x = g.kw; p.stride = g.stride; p.off_y = g.off_y; p.off_x = g.off_x;
+    p.out_sy = g.out_sy; p.out_sx = g.out_sx; p.out_oy = g.out_oy; p.out_ox = g.out_ox; p.out_H = g.out_H; p.out_W = g.out_W;
     // pixel patch per tile: TH x TW = 128 pixels; pick the shape that wastes the fewest out-of-image pixels
     {
         const int cand[5] = {16, 8, 32, 64, 128};
@@ -948,27 +981,47 @@ extern "C" int supir_conv3x3_bf16(const void* x, long long ldx, const void* Wp, 
     p.tiles_y = (H + p.TH - 1) / p.TH;
     p.num_m_tiles = B * p.tiles_x * p.tiles_y;
     p.kchunks = (Cin + BK - 1) / BK;
-    p.num_kb = 9 * p.kchunks;
-    p.M = B * H * Wd; p.N = Cout; p.K = 9 * Cin;
+    p.num_kb = ntaps * p.kchunks;
+    p.M = B * H * Wd; p.N = Cout; p.K = ntaps * Cin;
     int rc = fill_epilogue(p, ep, Cout);
     if (rc) return rc;
-    SUPIR_REQUIRE(ldc >= p.n_out, "supir_conv3x3_bf16: ldc %lld < output columns %d", ldc, p.n_out);
+    SUPIR_REQUIRE(ldc >= p.n_out, "%s: ldc %lld < output columns %d", who, ldc, p.n_out);
+    const bool plain_out = g.out_sy == 1 && g.out_sx == 1 && g.out_H == H && g.out_W == Wd;
+    SUPIR_REQUIRE(plain_out || (!p.residual && !p.rowvec), "%s: residual / per-image vector need a plain output layout", who);
+    SUPIR_REQUIRE(plain_out || (g.out_sy != 1 || g.out_sx != 1) || (g.out_H == H && g.out_W == Wd), "%s: unit-stride outputs must match the grid", who);
     p.out = out; p.ldc = ldc;
     const int bn = pick_bn(p, g_force_bn);
     CUtensorMap tmA, tmB;
     {
-        const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Wd, (uint64_t)H, (uint64_t)B};
-        const uint64_t str[3] = {(uint64_t)ldx, (uint64_t)ldx * Wd, (uint64_t)ldx * Wd * H};
-        const uint32_t box[4] = {BK, (uint32_t)p.TW, (uint32_t)p.TH, 1};
-        rc = make_tmap_bf16(&tmA, x, 4, dims, str, box);
+        // input [B, Hin, Win, Cin]; a tile's box covers TH x TW output pixels = every `stride`-th input pixel (elementStrides)
+        const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)B};
+        const uint64_t str[3] = {(uint64_t)ldx, (uint64_t)ldx * Win, (uint64_t)ldx * Win * Hin};
+        const uint32_t box[4] = {BK, (uint32_t)(p.TW * g.stride), (uint32_t)(p.TH * g.stride), 1};
+        const uint32_t est[4] = {1, (uint32_t)g.stride, (uint32_t)g.stride, 1};
+        rc = make_tmap_bf16_strided(&tmA, x, 4, dims, str, box, est);
         if (rc) return rc;
     }
     {
-        const uint64_t dims[2] = {(uint64_t)(9 * Cin), (uint64_t)Cout};
-        const uint64_t str[1] = {(uint64_t)(9 * Cin)};
+        const uint64_t dims[2] = {(uint64_t)(ntaps * Cin), (uint64_t)Cout};
+        const uint64_t str[1] = {(uint64_t)(ntaps * Cin)};
         const uint32_t box[2] = {BK, (uint32_t)(bn / pick_ctas(p, bn))};
         rc = make_tmap_bf16(&tmB, Wp, 2, dims, str, box);
         if (rc) return rc;
     }
     return run_gemm(tmA, tmB, p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int supir_conv_geom_bf16(const void* x, long long ldx, const void* Wp, void* out, long long ldc, int B, int Hin, int Win,
+                                    int Cin, int Cout, const supir_conv_geometry* geom, const supir_epilogue* ep, void* stream) {
+    SUPIR_REQUIRE(geom, "supir_conv_geom_bf16: null geometry");
+    return conv_geom_impl("supir_conv_geom_bf16", x, ldx, Wp, out, ldc, B, Hin, Win, Cin, Cout, *geom, ep, stream);
+}
+
+extern "C" int supir_conv3x3_bf16(const void* x, long long ldx, const void* Wp, void* out, long long ldc, int B, int H,
+                                  int Wd, int Cin, int Cout, const supir_epilogue* ep, void* stream) {
+    supir_conv_geometry g{};
+    g.kh = g.kw = 3; g.stride = 1; g.off_y = g.off_x = -1;
+    g.Hout = H; g.Wout = Wd;
+    g.out_sy = g.out_sx = 1; g.out_oy = g.out_ox = 0; g.out_H = H; g.out_W = Wd;
+    return conv_geom_impl("supir_conv3x3_bf16", x, ldx, Wp, out, ldc, B, H, Wd, Cin, Cout, g, ep, stream);
 }

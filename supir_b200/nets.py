@@ -187,11 +187,14 @@ class Downsample(nn.Module):
 
     def run(self, ctx, x: Act):
         Ho, Wo = (x.H + 2 - 3) // 2 + 1, (x.W + 2 - 3) // 2 + 1
-        cols = ctx.new(x.B * Ho * Wo, 9 * x.C)
-        ops.im2col_s2(x.t, x.B, x.H, x.W, cols, Ho, Wo, 1)
         out = ctx.new(x.B * Ho * Wo, self.out_channels)
-        ops.gemm(cols, self._w, out, bias=self._b)
-        ctx.free(cols)
+        if ops.CONV_GEOM:
+            ops.conv3x3_stride2(x.t, x.B, x.H, x.W, self._w, out, 1, bias=self._b)
+        else:
+            cols = ctx.new(x.B * Ho * Wo, 9 * x.C)
+            ops.im2col_s2(x.t, x.B, x.H, x.W, cols, Ho, Wo, 1)
+            ops.gemm(cols, self._w, out, bias=self._b)
+            ctx.free(cols)
         return Act(out, x.B, Ho, Wo)
 
 
@@ -206,14 +209,21 @@ class Upsample(nn.Module):
         self.conv = nn.Conv2d(channels, self.out_channels, 3, padding=1)
 
     def pack(self):
-        self._w, self._b = pack_conv3x3(self.conv.weight), _bias_bf16_values(self.conv.bias)
+        self._b = _bias_bf16_values(self.conv.bias)
+        if ops.CONV_GEOM:
+            self._wfold = ops.fold_upsample_weights(self.conv.weight)
+        else:
+            self._w = pack_conv3x3(self.conv.weight)
 
     def run(self, ctx, x: Act):
-        up = ctx.new(4 * x.rows, x.C)
-        ops.upsample2x(x.t, x.B, x.H, x.W, up)
         out = ctx.new(4 * x.rows, self.out_channels)
-        ops.conv3x3(up, x.B, 2 * x.H, 2 * x.W, self._w, out, bias=self._b)
-        ctx.free(up)
+        if ops.CONV_GEOM:      # four sub-pixel 2x2 convolutions on the low-resolution input: no 4x buffer, 2.25x fewer FLOPs
+            ops.upsample2x_conv3x3(x.t, x.B, x.H, x.W, self._wfold, out, bias=self._b)
+        else:
+            up = ctx.new(4 * x.rows, x.C)
+            ops.upsample2x(x.t, x.B, x.H, x.W, up)
+            ops.conv3x3(up, x.B, 2 * x.H, 2 * x.W, self._w, out, bias=self._b)
+            ctx.free(up)
         return Act(out, x.B, 2 * x.H, 2 * x.W)
 
 

@@ -9,7 +9,13 @@ import ctypes
 import torch
 
 from . import _native
-from ._native import Epilogue, call
+import os
+
+from ._native import ConvGeometry, Epilogue, call
+
+# strided / sub-pixel convolutions through the implicit-GEMM kernel's geometry mode (supir_conv_geom_bf16); "0" restores the
+# im2col buffer (stride 2) and the materialised nearest-2x upsample in front of a plain 3x3 convolution
+CONV_GEOM = os.environ.get("SUPIR_B200_CONV_GEOM", "1") != "0"
 
 BF16 = torch.bfloat16
 
@@ -106,6 +112,61 @@ def conv3x3(x, B, H, W, wp, out, bias=None, rowvec=None, residual=None, act=0):
     ep = _epilogue(bias, rowvec, 0, residual, act, out.dtype == torch.float32)
     call("supir_conv3x3_bf16", _ptr(x), x.stride(0), _ptr(wp), _ptr(out), out.stride(0), B, H, W, Cin, Cout,
          ctypes.byref(ep), _stream())
+    return out
+
+
+def conv_geom(x, B, Hin, Win, wp, out, geom, bias=None, act=0):
+    """General small-kernel convolution (see supir_conv_geometry): x [B*Hin*Win, Cin], wp [Cout, kh*kw*Cin], out [B*out_H*out_W, Cout]."""
+    _need_cuda(x, wp, out)
+    _mat(x), _mat(wp)
+    Cin, Cout = x.shape[1], wp.shape[0]
+    g = ConvGeometry(**geom)
+    assert x.shape[0] == B * Hin * Win and wp.shape[1] == g.kh * g.kw * Cin and wp.is_contiguous()
+    assert out.shape == (B * g.out_H * g.out_W, Cout), (out.shape, B, g.out_H, g.out_W, Cout)
+    ep = _epilogue(bias, None, 0, None, act, out.dtype == torch.float32)
+    call("supir_conv_geom_bf16", _ptr(x), x.stride(0), _ptr(wp), _ptr(out), out.stride(0), B, Hin, Win, Cin, Cout, ctypes.byref(g),
+         ctypes.byref(ep), _stream())
+    return out
+
+
+def conv3x3_stride2(x, B, H, W, wp, out, pad_lo, bias=None):
+    """3x3 stride-2 convolution: pad_lo = 1 is Conv2d(stride=2, padding=1) (openaimodel.py:196-210); pad_lo = 0 is the VAE's
+    F.pad(0,1,0,1) + Conv2d(stride=2, padding=0) (model.py:81-85). The TMA gathers every second input pixel: no im2col."""
+    Ho, Wo = (H + 2 * pad_lo - 3) // 2 + 1 if pad_lo else (H + 1 - 3) // 2 + 1, (W + 2 * pad_lo - 3) // 2 + 1 if pad_lo else (W + 1 - 3) // 2 + 1
+    geom = dict(kh=3, kw=3, stride=2, off_y=-pad_lo, off_x=-pad_lo, Hout=Ho, Wout=Wo, out_sy=1, out_sx=1, out_oy=0, out_ox=0,
+                out_H=Ho, out_W=Wo)
+    return conv_geom(x, B, H, W, wp, out, geom, bias=bias)
+
+
+def fold_upsample_weights(w):
+    """[Cout, Cin, 3, 3] -> four packed [Cout, 2*2*Cin] bf16 matrices, index py*2+px: a 3x3 convolution of the nearest-2x
+    upsampled image equals, for the output pixels of parity (py, px), a 2x2 convolution of the LOW-resolution image whose taps
+    are sums of the 3x3 taps that fall on the same source pixel (rows: py=0 -> {0},{1,2}; py=1 -> {0,1},{2}; same for columns)."""
+    wf = w.detach().to(BF16).to(torch.float32)             # the values the reference's bf16 convolution multiplies
+    sets = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}
+    out = []
+    for py in (0, 1):
+        for px in (0, 1):
+            taps = []
+            for a in (0, 1):
+                for b in (0, 1):
+                    acc = 0
+                    for ky in sets[py][a]:
+                        for kx in sets[px][b]:
+                            acc = acc + wf[:, :, ky, kx]
+                    taps.append(acc)                        # [Cout, Cin]
+            out.append(torch.stack(taps, 1).reshape(w.shape[0], -1).to(BF16).contiguous())
+    return out
+
+
+def upsample2x_conv3x3(x, B, H, W, wfold, out, bias=None):
+    """conv3x3(nearest_2x(x)) (openaimodel.py:131-151; model.py:64-68) as four sub-pixel 2x2 convolutions on x [B*H*W, Cin]
+    writing the interleaved pixels of out [B*2H*2W, Cout]; wfold from fold_upsample_weights."""
+    for py in (0, 1):
+        for px in (0, 1):
+            geom = dict(kh=2, kw=2, stride=1, off_y=py - 1, off_x=px - 1, Hout=H, Wout=W, out_sy=2, out_sx=2, out_oy=py, out_ox=px,
+                        out_H=2 * H, out_W=2 * W)
+            conv_geom(x, B, H, W, wfold[py * 2 + px], out, geom, bias=bias)
     return out
 
 

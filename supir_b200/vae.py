@@ -133,7 +133,8 @@ class _VAENet(nn.Module):
                     resblock(blk)
                 if lvl != 0:
                     c = self.up[lvl].upsample.conv
-                    add(("upsample", pack_conv3x3(c.weight), _bias_bf16_values(c.bias), c.out_channels))
+                    add(("upsample", ops.fold_upsample_weights(c.weight) if ops.CONV_GEOM else pack_conv3x3(c.weight),
+                         _bias_bf16_values(c.bias), c.out_channels))
         else:
             for lvl in range(self.num_resolutions):
                 for blk in self.down[lvl].block:
@@ -177,19 +178,27 @@ class _VAENet(nn.Module):
             pool.put(a.t, r)
             tile["h"] = Act(out, a.B, a.H, a.W)
         elif kind == "upsample":
-            up = pool.get((4 * a.rows, a.C))
-            ops.upsample2x(a.t, a.B, a.H, a.W, up)
             out = pool.get((4 * a.rows, step[3]))
-            ops.conv3x3(up, a.B, 2 * a.H, 2 * a.W, step[1], out, bias=step[2])
-            pool.put(up, a.t)
+            if ops.CONV_GEOM:
+                ops.upsample2x_conv3x3(a.t, a.B, a.H, a.W, step[1], out, bias=step[2])
+            else:
+                up = pool.get((4 * a.rows, a.C))
+                ops.upsample2x(a.t, a.B, a.H, a.W, up)
+                ops.conv3x3(up, a.B, 2 * a.H, 2 * a.W, step[1], out, bias=step[2])
+                pool.put(up)
+            pool.put(a.t)
             tile["h"] = Act(out, a.B, 2 * a.H, 2 * a.W)
         elif kind == "downsample":       # pad (0,1,0,1), stride 2, no conv padding (model.py:81-85)
             Ho, Wo = (a.H + 1 - 3) // 2 + 1, (a.W + 1 - 3) // 2 + 1
-            cols = pool.get((a.B * Ho * Wo, 9 * a.C))
-            ops.im2col_s2(a.t, a.B, a.H, a.W, cols, Ho, Wo, 0)
             out = pool.get((a.B * Ho * Wo, step[3]))
-            ops.gemm(cols, step[1], out, bias=step[2])
-            pool.put(cols, a.t)
+            if ops.CONV_GEOM:
+                ops.conv3x3_stride2(a.t, a.B, a.H, a.W, step[1], out, 0, bias=step[2])
+            else:
+                cols = pool.get((a.B * Ho * Wo, 9 * a.C))
+                ops.im2col_s2(a.t, a.B, a.H, a.W, cols, Ho, Wo, 0)
+                ops.gemm(cols, step[1], out, bias=step[2])
+                pool.put(cols)
+            pool.put(a.t)
             tile["h"] = Act(out, a.B, Ho, Wo)
         elif kind == "attn":
             self._attn(pool, step, tile, add_res)

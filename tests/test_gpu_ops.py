@@ -349,3 +349,28 @@ def test_gemm_with_folded_layernorm(M, C, N, with_res):
             close(out.float().cpu(), ref, 4e-2, 3e-2)
     finally:
         lib.supir_debug_force_direct_epilogue(0)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 32, 32, 64, 96), (1, 37, 51, 128, 128), (3, 16, 24, 320, 320), (1, 150, 150, 64, 64)])
+def test_strided_and_subpixel_convs(B, H, W, Cin, Cout):
+    """supir_conv_geom_bf16: 3x3 stride 2 with pad 1 (openaimodel.py:196-210) and with the VAE's (0,1,0,1) padding
+    (model.py:81-85) via TMA element strides; nearest-2x + 3x3 (openaimodel.py:131-151) as four sub-pixel 2x2 convolutions."""
+    ops = _ops()
+    x = rnd((B, Cin, H, W), 101).to(BF)
+    w = (rnd((Cout, Cin, 3, 3), 102) / (9 * Cin) ** 0.5).to(BF)
+    b = (rnd((Cout,), 103) * 0.1).to(BF).float()
+    xt = nhwc(x.float())
+    wp = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous().cuda()
+    for pad_lo in (1, 0):
+        if pad_lo:
+            ref = F.conv2d(x.float(), w.float(), b, stride=2, padding=1)
+        else:
+            ref = F.conv2d(F.pad(x.float(), (0, 1, 0, 1)), w.float(), b, stride=2, padding=0)
+        Ho, Wo = ref.shape[2], ref.shape[3]
+        out = torch.full((B * Ho * Wo, Cout), float("nan"), dtype=BF, device="cuda")
+        ops.conv3x3_stride2(xt, B, H, W, wp, out, pad_lo, bias=b.cuda())
+        close(from_nhwc(out, B, Ho, Wo), ref, 3e-2)
+    ref = F.conv2d(F.interpolate(x.float(), scale_factor=2, mode="nearest"), w.float(), b, padding=1)
+    out = torch.full((B * 4 * H * W, Cout), float("nan"), dtype=BF, device="cuda")
+    ops.upsample2x_conv3x3(xt, B, H, W, [m.cuda() for m in ops.fold_upsample_weights(w.float())], out, bias=b.cuda())
+    close(from_nhwc(out, B, 2 * H, 2 * W), ref, 3e-2)

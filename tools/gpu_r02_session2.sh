@@ -12,6 +12,9 @@ run() {  # run <timeout_s> <logfile> <command...>
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/r02_s2_smi.txt 2>&1
 run 90 r02_selftest_attnquick.log tools/selftest attnquick || { tail -n 30 gpurun_out/r02_selftest_attnquick.log; echo "HANG GUARD FAILED - stopping"; exit 1; }
 tail -n 8 gpurun_out/r02_selftest_attnquick.log
+# geometry-mode convolutions (TMA element strides): if this does not pass, the rest of the session uses the im2col / upsample path
+if run 150 r02_pytest_conv_geom.log python -m pytest tests/test_gpu_ops.py -q -m gpu -k "strided_and_subpixel" -s --timeout 100; then echo "conv geometry: ok"; else
+  tail -n 20 gpurun_out/r02_pytest_conv_geom.log; echo "conv geometry FAILED: continuing with SUPIR_B200_CONV_GEOM=0"; export SUPIR_B200_CONV_GEOM=0; fi
 run 200 r02_selftest_attn.log tools/selftest attn; tail -n 12 gpurun_out/r02_selftest_attn.log
 run 200 r02_selftest_attnperf2.log tools/selftest attnperf2; cat gpurun_out/r02_selftest_attnperf2.log
 run 200 r02_selftest_epiperf.log tools/selftest epiperf; cat gpurun_out/r02_selftest_epiperf.log
