@@ -510,12 +510,17 @@ def run_supir(args):
     clocks.mark()
     lc0 = _native.launch_count() + net.replayed_launches
     barrier()
+    prof = os.environ.get("SUPIR_BENCH_CUDA_PROFILER", "0") == "1"     # `ncu --profile-from-start off`: capture the timed steps only
     t0, t1 = ev(), ev()
+    if prof:
+        torch.cuda.profiler.start()
     t0.record()
     for i in range(args.warmup, args.warmup + args.steps):
         run.step(i % nsteps)
     t1.record()
     barrier()
+    if prof:
+        torch.cuda.profiler.stop()
     step_ms = t0.elapsed_time(t1) / args.steps
     lc1 = _native.launch_count() + net.replayed_launches
     clk = clocks.stop() if rank == 0 else None

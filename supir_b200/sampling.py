@@ -108,9 +108,17 @@ class FusedDenoiser:
 
     def __init__(self, denoiser, network):
         self.denoiser, self.network = denoiser, network
+        self._tokens = bool(getattr(network, "supports_context_token", False))
 
     def __call__(self, input, sigma, c, control_scale):
         return self.denoiser(self.network, input, sigma, c, control_scale)
+
+    def run_network(self, x, t, c, control_scale, context_token=None):
+        """network(x, t, c, control_scale); the token (a name for the content of c['crossattn'], constant over a sampler run)
+        is forwarded only to networks that understand it (supir_b200.wrappers.ControlWrapper)."""
+        if self._tokens and context_token is not None:
+            return self.network(x, t, c, control_scale, context_token=context_token)
+        return self.network(x, t, c, control_scale)
 
 
 class BaseDiffusionSampler:
@@ -170,7 +178,7 @@ class RestoreEDMSampler(BaseDiffusionSampler):
             ops.edm_pre(x, eps if k["gamma"] > 0 else None, k["noise_mul"], c_in, x_hat, net_in)
             cpair = {key: torch.cat((uc[key], cond[key]), 0) for key in ("vector", "crossattn", "control")}
             t = torch.full((2 * N,), idx, dtype=torch.long, device=x.device)
-            net_out = denoiser.network(net_in, t, cpair, k["control_scale"], context_token=k.get("context_token"))
+            net_out = denoiser.run_network(net_in, t, cpair, k["control_scale"], k.get("context_token"))
             x_next = torch.empty_like(x)
             ops.edm_post(x_hat, net_out, x_center if k["use_restore"] else None, -sq, self.guider.scale_host(k["sigma_hat"]),
                          k["restore_mul"], k["sigma_hat"], k["dt"], x_next)
@@ -258,8 +266,8 @@ class _EDMRun:
         for u in range(self.lo, self.hi):            # unit 0: unconditional rows, unit 1: conditional rows
             c = self.uc if u == 0 else self.cond
             t = torch.full((N,), idx, dtype=torch.long, device=x.device)
-            out = self.denoiser.network(net_in[u * N:(u + 1) * N], t, {key: c[key] for key in ("vector", "crossattn", "control")},
-                                        k["control_scale"], context_token=(self.uid, u))
+            out = self.denoiser.run_network(net_in[u * N:(u + 1) * N], t, {key: c[key] for key in ("vector", "crossattn", "control")},
+                                            k["control_scale"], (self.uid, u))
             self.pair_out[self.rank * self.per + (u - self.lo)] = out
         exchange_unit_outputs(self.pair_out, self.rank, self.per, self.group)
         if self.per * self.world == 2:
@@ -421,8 +429,8 @@ class _TiledRun:
                 g = g1 - g0
                 cg = {"control": self.u_lq[g0 * b:g1 * b], "crossattn": self.u_ctx[g0 * b:g1 * b], "vector": self.u_vec[g0 * b:g1 * b]}
                 t = torch.full((g * b,), idx, dtype=torch.long, device=x.device)
-                out = self.denoiser.network(net_in[self.lo + g0:self.lo + g1].reshape(g * b, ch, T, T), t, cg, k["control_scale"],
-                                            context_token=(self.uid, g0))   # the conditioning is constant over this run's steps
+                out = self.denoiser.run_network(net_in[self.lo + g0:self.lo + g1].reshape(g * b, ch, T, T), t, cg, k["control_scale"],
+                                                (self.uid, g0))       # the conditioning is constant over this run's steps
                 self.units_pad[slot0 + g0:slot0 + g1] = out.view(g, b, ch, T, T)
         if self.world > 1:
             # the ONE exchange of a step: every rank receives the raw network outputs of all units (NCCL all-gather over NVLink)

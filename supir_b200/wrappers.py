@@ -75,6 +75,8 @@ class _Plan:
 
 
 class ControlWrapper(nn.Module):
+    supports_context_token = True       # forward(..., context_token=) — see FusedDenoiser.run_network
+
     def __init__(self, diffusion_model, compile_model: bool = False, dtype=torch.float32):
         super().__init__()
         self.diffusion_model = diffusion_model

@@ -33,7 +33,7 @@ def breakdown(w, B, hw):
     import inspect, collections
     from supir_b200 import ops
     names = [n for n, f in vars(ops).items() if inspect.isfunction(f) and f.__module__ == ops.__name__ and not n.startswith("_")
-             and n not in ("groupnorm_ws_size",)]
+             and n not in ("groupnorm_ws_size", "upsample2x_conv3x3", "conv3x3_stride2", "fold_upsample_weights", "fold_layernorm")]
     rec, orig = [], {}
     for n in names:
         f = orig[n] = getattr(ops, n)
