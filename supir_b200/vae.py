@@ -373,23 +373,35 @@ class _VAENet(nn.Module):
                 self._finish_tile(pool, tiles[i], result[:, :, ob[2]:ob[3], ob[0]:ob[1]], crop=(y0, x0, y1 - y0, x1 - x0))
             return result
         # sharded: every rank packs its cropped tiles back to back; one all-gather; paste
-        numel = [N * Cout * (c[1] - c[0]) * (c[3] - c[2]) for c in crops]
-        offs, fill = {}, [0] * world
-        for i in range(T):
-            offs[i] = fill[i % world]
-            fill[i % world] += numel[i]
-        slot = max(fill)
+        numel, offs, slot = plan_packed_crops(crops, N * Cout, world)
         packed = torch.empty((world, slot), dtype=torch.float32, device=dev)
         for i in mine:
             y0, y1, x0, x1 = crops[i]
             view = packed[rank, offs[i]:offs[i] + numel[i]].view(N, Cout, y1 - y0, x1 - x0)
             self._finish_tile(pool, tiles[i], view, crop=(y0, x0, y1 - y0, x1 - x0))
         dist.all_gather_into_tensor(packed.view(-1), packed[rank].clone(), group=group)
-        for i in range(T):
-            y0, y1, x0, x1 = crops[i]
-            ob = out_bboxes[i]
-            result[:, :, ob[2]:ob[3], ob[0]:ob[1]].copy_(packed[i % world, offs[i]:offs[i] + numel[i]].view(N, Cout, y1 - y0, x1 - x0))
+        paste_packed_crops(result, packed, crops, out_bboxes, numel, offs, world)
         return result
+
+
+def plan_packed_crops(crops, planes, world):
+    """Layout of the sharded tiled VAE's output exchange: tile i (owner i % world) stores its cropped output, `planes` x
+    (y1-y0) x (x1-x0) floats, back to back in its owner's slot. Returns (numel per tile, offset per tile, slot length)."""
+    numel = [planes * (c[1] - c[0]) * (c[3] - c[2]) for c in crops]
+    offs, fill = [0] * len(crops), [0] * world
+    for i in range(len(crops)):
+        offs[i] = fill[i % world]
+        fill[i % world] += numel[i]
+    return numel, offs, max(fill)
+
+
+def paste_packed_crops(result, packed, crops, out_bboxes, numel, offs, world):
+    """Inverse of the packing: result[:, :, output box of tile i] = tile i's crop (tilevae.py:946-948 pastes the same boxes)."""
+    N, Cout = result.shape[:2]
+    for i, (y0, y1, x0, x1) in enumerate(crops):
+        ob = out_bboxes[i]
+        result[:, :, ob[2]:ob[3], ob[0]:ob[1]].copy_(packed[i % world, offs[i]:offs[i] + numel[i]].view(N, Cout, y1 - y0, x1 - x0))
+    return result
 
 
 def get_best_tile_size(lowerbound, upperbound):

@@ -92,6 +92,49 @@ def test_sharded_units_all_gather_equals_single_process(world):
     assert sum(r[2] for r in res) == 14 and max(r[2] for r in res) - min(r[2] for r in res) <= 1
 
 
+def _vae_worker(rank, world, port, q):
+    """Tiled-VAE output exchange: round-robin tiles, crops packed back to back per rank, one all-gather, paste."""
+    import torch.distributed as dist
+    from supir_b200 import vae
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ok = True
+    for (h, w, ts, dec) in [(40, 52, 16, True), (192, 160, 64, False), (75, 33, 16, True)]:
+        N, C = 1, 3
+        in_b, out_b = vae.split_tiles(h, w, ts, dec)
+        sc = (lambda v: v * 8) if dec else (lambda v: v // 8)
+        dims = [((b[3] - b[2]) * 8, (b[1] - b[0]) * 8) if dec else ((b[3] - b[2]) // 8, (b[1] - b[0]) // 8) for b in in_b]
+        crops = [vae.crop_margins(dims[i][0], dims[i][1], in_b[i], out_b[i], dec) for i in range(len(in_b))]
+        canvas = torch.randn((N, C, sc(h), sc(w)), generator=torch.Generator().manual_seed(5))
+        numel, offs, slot = vae.plan_packed_crops(crops, N * C, world)
+        packed = torch.zeros((world, slot))
+        for i in range(len(in_b)):
+            if i % world == rank:
+                ob = out_b[i]
+                packed[rank, offs[i]:offs[i] + numel[i]] = canvas[:, :, ob[2]:ob[3], ob[0]:ob[1]].reshape(-1)
+        dist.all_gather_into_tensor(packed.view(-1), packed[rank].clone())
+        result = torch.full_like(canvas, float("nan"))
+        vae.paste_packed_crops(result, packed, crops, out_b, numel, offs, world)
+        ok = ok and bool(torch.equal(result, canvas))
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_vae_cropped_tile_exchange_reassembles_the_canvas(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_vae_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r[0] for r in res) == list(range(world)) and all(r[1] for r in res), res
+
+
 @pytest.mark.parametrize("world", [2])
 def test_sharded_windows_all_gather_equals_single_process(world):
     ctx = mp.get_context("spawn")
