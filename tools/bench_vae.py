@@ -7,8 +7,8 @@ from supir_b200 import ops, vae
 
 VAE_CFG = dict(attn_type="vanilla-xformers", double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128,
                ch_mult=[1, 2, 4, 4], num_res_blocks=2, attn_resolutions=[], dropout=0.0)
-NAMES = ["conv3x3", "gemm", "groupnorm_stats", "groupnorm_apply", "groupnorm_finalize", "groupnorm_merge_tiles", "upsample2x",
-         "axpy", "copy2d", "conv3x3_small_cin", "conv3x3_small_cout", "im2col_s2", "softmax_rows"]
+NAMES = ["conv3x3", "conv_geom", "gemm", "attention_1head", "groupnorm_stats", "groupnorm_apply", "groupnorm_finalize", "groupnorm_merge_tiles",
+         "upsample2x", "axpy", "copy2d", "conv3x3_small_cin", "conv3x3_small_cout", "im2col_s2", "softmax_rows"]
 
 
 def instrument(rec):
