@@ -85,8 +85,9 @@ int supir_set_gemm_tile_n(int bn);
  * also settable through the environment variable SUPIR_B200_GEMM_PAIR), 2 = pairs whenever the tile is 256 wide */
 int supir_set_gemm_pair_mode(int on);
 /* tuning knob for the staged epilogue: 0 = one TMA load / store per 128-row chunk, issued by one thread of each 4-warp group
- * behind two named barriers (default); 1 = every epilogue warp moves its own 32 rows with its own TMA operations and
- * mbarriers, no cross-warp barrier in the chunk loop; negative = environment (SUPIR_B200_GEMM_WARP_EPILOGUE) / default. */
+ * behind two named barriers; 1 = every epilogue warp moves its own 32 rows with its own TMA operations and mbarriers, no
+ * cross-warp barrier in the chunk loop; negative = environment (SUPIR_B200_GEMM_WARP_EPILOGUE) or, by default, automatic:
+ * per-warp for every epilogue except GEGLU (measured: profiles/r02_selftest_epiperf.log). */
 int supir_set_gemm_epilogue_mode(int per_warp);
 /* debugging: 1 routes every GEMM through the direct-store epilogue instead of the shared-memory + TMA-store one */
 int supir_debug_force_direct_epilogue(int on);
@@ -175,7 +176,8 @@ int supir_debug_set_attention_descriptors(long long smem_desc_template, long lon
 int supir_attention_1head_bf16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                                void* out, long long ldo, int B, int L, int head_dim, float scale, void* stream);
 /* tuning knob: how many of every 4 element pairs of the softmax take 2^x from the FMA-pipe polynomial instead of MUFU.EX2
- * (0..4; default 2 or the environment variable SUPIR_B200_ATTN_EMU; negative restores the default). */
+ * (0..4; default 0 = all on MUFU, which measured fastest on B200, or the environment variable SUPIR_B200_ATTN_EMU; negative
+ * restores the default). */
 int supir_set_attention_exp_emulation(int pairs_of_4);
 
 /* ------------------------------------------------------------------------------------------------------------------ */

@@ -21,7 +21,8 @@
 // The softmax is the bound of this kernel, not the MMA: at head_dim 64 a key block costs 512 tensor-pipe cycles per tile but
 // 128 ex2 per row = 1024 MUFU cycles per warp (MUFU: 4 lanes/clk per SM sub-partition). So
 //   * the arithmetic around the exponential runs on PACKED fp32 pairs (fma/add.f32x2 -> FFMA2/FADD2: half the issue slots);
-//   * EMU of every 4 element pairs take their exponential on the FMA pipe instead of MUFU: Cody-Waite split
+//   * (optional, OFF by default — it measured slower on B200, see attention_emu()) EMU of every 4 element pairs can take
+//     their exponential on the FMA pipe instead of MUFU: Cody-Waite split
 //     x = n + f (add.rm with the 1.5*2^23 magic constant), degree-3 minimax polynomial for 2^f on [0,1) (max rel. error
 //     8.8e-5 = 2^-13.5, far below the bf16 rounding of P at 2^-9), exponent reinserted with one integer shift-add;
 //   * the row maximum uses 3-input FMNMX3; online softmax never touches O in the common case: the exponent reference m is
@@ -411,8 +412,11 @@ static int g_att_emu = -1;            // emulated exponent pairs per 4: -1 = env
 static int attention_emu() {
     if (g_att_emu < 0) {
         const char* e = getenv("SUPIR_B200_ATTN_EMU");
-        g_att_emu = e ? atoi(e) : 2;
-        if (g_att_emu < 0 || g_att_emu > 4) g_att_emu = 2;
+        // default 0: on B200 the emulated pairs measured SLOWER than MUFU (profiles/r02_selftest_attnperf2.log: 817 / 808 / 740 /
+        // 652 / 568 TFLOP/s at 4096 tokens for 0..4 of 4 pairs) — the packed FFMA2 / FADD2 chain costs more issue and FMA-pipe
+        // time than the 16 MUFU cycles per pair it saves
+        g_att_emu = e ? atoi(e) : 0;
+        if (g_att_emu < 0 || g_att_emu > 4) g_att_emu = 0;
     }
     return g_att_emu;
 }
@@ -445,11 +449,11 @@ template <int TILES, int STAGES, int NKEY>
 static int launch_attention_emu(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnParams& p, int B,
                                 cudaStream_t st) {
     switch (attention_emu()) {
-        case 0: return launch_attention<TILES, STAGES, NKEY, 0>(tmQ, tmK, tmV, p, B, st);
         case 1: return launch_attention<TILES, STAGES, NKEY, 1>(tmQ, tmK, tmV, p, B, st);
         case 3: return launch_attention<TILES, STAGES, NKEY, 3>(tmQ, tmK, tmV, p, B, st);
         case 4: return launch_attention<TILES, STAGES, NKEY, 4>(tmQ, tmK, tmV, p, B, st);
-        default: return launch_attention<TILES, STAGES, NKEY, 2>(tmQ, tmK, tmV, p, B, st);
+        case 2: return launch_attention<TILES, STAGES, NKEY, 2>(tmQ, tmK, tmV, p, B, st);
+        default: return launch_attention<TILES, STAGES, NKEY, 0>(tmQ, tmK, tmV, p, B, st);
     }
 }
 
@@ -568,8 +572,12 @@ attention_d512_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     uint64_t* slot_empty = slot_full + A5_SLOTS;        // [A5_SLOTS]
     uint64_t* s_full = slot_empty + A5_SLOTS;           // [2] per S buffer
     uint64_t* p_full = s_full + 2;                      // [2]
-    uint64_t* pv_done = p_full + 2;                     // 1
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 1);
+    // PV(j) commits pv_done[j & 1]. Two barriers because the softmax warps wait on PV only when they rescale O and at the
+    // very end: with ONE barrier flipping every block, a waiter two blocks behind would mistake an older phase for the one
+    // it wants (mbarrier waits carry one parity bit). Per parity of j the waiter is at most one phase behind: PV(j-3) has
+    // retired before S(j) could be delivered, and PV(j+1) cannot start before P(j+1) exists.
+    uint64_t* pv_done = p_full + 2;                     // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * ATT_BM, half = blockIdx.y, batch = blockIdx.z;
@@ -581,8 +589,7 @@ attention_d512_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         tma_prefetch_desc(&tmV);
         mbar_init(q_full, 1);
         for (int s = 0; s < A5_SLOTS; ++s) { mbar_init(&slot_full[s], 1); mbar_init(&slot_empty[s], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); }
-        mbar_init(pv_done, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1); }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -657,7 +664,7 @@ attention_d512_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                     umma_commit(&slot_empty[slot]);
                     next_slot();
                 }
-                umma_commit(pv_done);
+                umma_commit(&pv_done[buf]);
             }
         }
       }
@@ -700,7 +707,7 @@ attention_d512_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             } else {
                 const bool need = mx > m_ref + ATT_RESCALE_THRESHOLD;
                 if (__any_sync(0xffffffffu, need)) {
-                    mbar_wait(pv_done, (j - 1) & 1);               // PV(j-1) is the last writer of O
+                    mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);   // PV(j-1) is the last writer of O
                     tc_fence_after();
                     const float alpha = need ? ex2_approx(m_ref - mx) : 1.0f;
                     if (need) m_ref = mx;
@@ -723,7 +730,7 @@ attention_d512_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[buf]);
         }
-        mbar_wait(pv_done, (nblk - 1) & 1);
+        mbar_wait(&pv_done[(nblk - 1) & 1], ((nblk - 1) >> 1) & 1);
         tc_fence_after();
         const int qrow = q0 + row;
         const float inv = 1.f / l_run;
@@ -804,10 +811,10 @@ extern "C" int supir_attention_1head_bf16(const void* q, long long ldq, const vo
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int emu = attention_emu();
     if (head_dim == 512) {
-        if (emu == 0) return launch_attention_d512<512, 0>(tmQ, tmK, tmV, p, B, st);
+        if (emu == 2) return launch_attention_d512<512, 2>(tmQ, tmK, tmV, p, B, st);
         if (emu == 4) return launch_attention_d512<512, 4>(tmQ, tmK, tmV, p, B, st);
-        return launch_attention_d512<512, 2>(tmQ, tmK, tmV, p, B, st);
+        return launch_attention_d512<512, 0>(tmQ, tmK, tmV, p, B, st);
     }
-    if (head_dim == 256) return launch_attention_d512<256, 2>(tmQ, tmK, tmV, p, B, st);
-    return launch_attention_d512<128, 2>(tmQ, tmK, tmV, p, B, st);
+    if (head_dim == 256) return launch_attention_d512<256, 0>(tmQ, tmK, tmV, p, B, st);
+    return launch_attention_d512<128, 0>(tmQ, tmK, tmV, p, B, st);
 }

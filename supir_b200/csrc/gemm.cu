@@ -787,13 +787,15 @@ long long g_desc_override = -1;   // debug: full 64-bit descriptor template (add
 long long g_idesc_override = -1;  // debug: instruction descriptor, -1 = default
 
 int g_force_direct_epilogue = 0;   // debug: 1 disables the staged (smem + TMA store) epilogue
-int g_warp_epilogue = -1;          // staged epilogue: 0 = one TMA op per 128-row chunk (named barriers), 1 = per-warp 32-row TMA ops; -1 = env/default
+int g_warp_epilogue = -1;          // staged epilogue: 0 = one TMA op per 128-row chunk (named barriers), 1 = per-warp 32-row TMA ops; -1 = env / automatic
+static int g_warp_epilogue_env = -2;
 static int gemm_epilogue_mode() {
-    if (g_warp_epilogue < 0) {
+    if (g_warp_epilogue >= 0) return g_warp_epilogue;
+    if (g_warp_epilogue_env == -2) {
         const char* e = getenv("SUPIR_B200_GEMM_WARP_EPILOGUE");
-        g_warp_epilogue = e ? (atoi(e) != 0) : 0;
+        g_warp_epilogue_env = e ? (atoi(e) != 0) : -1;
     }
-    return g_warp_epilogue;
+    return g_warp_epilogue_env;
 }
 
 // staged epilogue applies to bf16 outputs with 16-byte aligned rows; it needs the per-image vector to be uniform per tile
@@ -840,7 +842,10 @@ static int run_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmKernelPa
     CUtensorMap tmC = tmA, tmR = tmA;   // placeholders when the direct epilogue is used
     p.staged = can_stage(p) ? 1 : 0;
     p.has_res = (p.staged && p.residual) ? 1 : 0;
-    p.warp_epi = (p.staged && gemm_epilogue_mode()) ? 1 : 0;
+    // per-warp TMA epilogue: +6..21 % on the bias / residual epilogues of the step's GEMMs, -2..5 % on GEGLU (whose chunks are
+    // 16 columns wide: 1 KB per warp and store) — profiles/r02_selftest_epiperf.log. -1 = that rule; 0 / 1 force a mode.
+    const int em = gemm_epilogue_mode();
+    p.warp_epi = (p.staged && (em < 0 ? p.act != 2 : em != 0)) ? 1 : 0;
     if (p.staged) {
         const int rc = make_epi_maps(p, &tmC, &tmR);
         if (rc) return rc;
