@@ -14,6 +14,7 @@ namespace supir {
 int set_error(int code, const char* fmt, ...);
 void count_launch(int n = 1);  // bumps the counter behind supir_launch_count()
 int device_sm_count();
+int current_device_slot();   // cudaGetDevice() clamped to [0, 63]: index of the per-device caches
 
 #define SUPIR_OK 0
 #define SUPIR_ERR_INVALID -1

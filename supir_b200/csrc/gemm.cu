@@ -663,15 +663,21 @@ int make_tmap_bf16_strided(CUtensorMap* m, const void* base, int rank, const uin
     return SUPIR_OK;
 }
 
+// current device, clamped into the per-device caches below (function attributes and SM counts are per device)
+int current_device_slot() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev < 0 ? 0 : (dev > 63 ? 63 : dev);
+}
+
 int device_sm_count() {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
+    static int sms[64] = {};
+    const int d = current_device_slot();
+    if (sms[d] == 0) {
+        cudaDeviceGetAttribute(&sms[d], cudaDevAttrMultiProcessorCount, d);
+        if (sms[d] <= 0) sms[d] = 148;
     }
-    return sms;
+    return sms[d];
 }
 
 extern int g_force_bn;
@@ -706,10 +712,11 @@ template <int BN, int CTAS>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
                        GemmKernelParams p, cudaStream_t st) {
     using S = GemmSmem<BN, CTAS>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};
+    const int dslot = current_device_slot();
+    if (!attr_set[dslot]) {
         SUPIR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-        attr_set = true;
+        attr_set[dslot] = true;
     }
     p.num_n_tiles = (p.N + BN - 1) / BN;
     p.nimg = p.conv ? (int)(p.M / ((long long)p.H * p.W)) : 0;

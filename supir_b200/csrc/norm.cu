@@ -9,6 +9,7 @@
 #include "supir_b200.h"
 
 namespace supir {
+int current_device_slot();
 
 // ---------------------------------------------------------------------------------------------
 // GroupNorm statistics: per (image, group) sum and sum of squares in fp64 — deterministic (no floating-point atomics):
@@ -449,7 +450,8 @@ extern "C" int supir_groupnorm_stats(const void* x, long long ldx, int B, int HW
     SUPIR_CHECK_CUDA(cudaMemsetAsync(ws + need - B, 0, sizeof(double) * B, st));   // tickets
     const int kp = threads / (C >> 3);
     const size_t smem = (size_t)2 * kp * C * sizeof(float);
-    static size_t max_set = 0;
+    static size_t max_set_dev[64] = {};
+    size_t& max_set = max_set_dev[current_device_slot()];
     if (smem > 48 * 1024 && smem > max_set) {
         SUPIR_CHECK_CUDA(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         max_set = smem;
@@ -567,7 +569,8 @@ extern "C" int supir_softmax_rows(const float* S, long long lds, void* P, long l
     const bool aligned = (lds % 4 == 0) && (ldp % 8 == 0) && (reinterpret_cast<uintptr_t>(S) % 16 == 0) &&
                          (reinterpret_cast<uintptr_t>(P) % 16 == 0);
     if (aligned && cols >= 1024 && smem <= 200 * 1024) {
-        static size_t max_set = 0;
+        static size_t max_set_dev[64] = {};
+    size_t& max_set = max_set_dev[current_device_slot()];
         if (smem > 48 * 1024 && smem > max_set) {
             SUPIR_CHECK_CUDA(cudaFuncSetAttribute(softmax_rows_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             max_set = smem;

@@ -10,6 +10,7 @@
 #include "supir_b200.h"
 
 namespace supir {
+int current_device_slot();
 
 // -------- Cin <= 8 : thread = (pixel, 8 output channels); weights in shared memory as [Cin*9][Cout] --------
 __global__ void conv3x3_small_cin_kernel(const float* __restrict__ x, long long sb, long long sc, long long sy,
@@ -178,7 +179,8 @@ extern "C" int supir_conv3x3_small_cin(const float* x, long long sb, long long s
     SUPIR_REQUIRE(Cin >= 1 && Cin <= 8 && Cout % 8 == 0 && ldo % 8 == 0, "supir_conv3x3_small_cin: Cin=%d Cout=%d unsupported", Cin, Cout);
     const size_t smem = (size_t)Cin * 9 * Cout * sizeof(float);
     SUPIR_REQUIRE(smem <= 160 * 1024, "supir_conv3x3_small_cin: weights do not fit shared memory");
-    static size_t max_set = 0;
+    static size_t max_set_dev[64] = {};
+    size_t& max_set = max_set_dev[current_device_slot()];
     if (smem > 48 * 1024 && smem > max_set) {
         SUPIR_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_small_cin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         max_set = smem;

@@ -80,3 +80,49 @@ def test_context_token_reuses_text_kv_only_for_the_same_token():
         xs = randn((2, 4, side, side), 5).cuda()
         w(xs, t, dict(c1, control=xs), control_scale=1.0)
     assert len(w._plans) == 2 and (2, 8, 8, 77) not in w._plans
+
+
+def test_reference_style_denoiser_lambda_matches_fused_path(monkeypatch):
+    """The reference hands the sampler an opaque lambda (SUPIR_model.py:123-130: `lambda input, sigma, c, control_scale:
+    self.denoiser(self.model, input, sigma, c, control_scale)`); this package's engine hands it a FusedDenoiser. Both drive
+    the REAL ControlWrapper here (full-width depth-1 networks), untiled and tiled; the two paths differ only in where the
+    fp32 step arithmetic is rounded (separate axpby / cfg_combine kernels vs the fused edm_pre / edm_post)."""
+    from supir_b200 import denoiser as dn, sampling
+    g = np.load(os.path.join(G, "unet_fullwidth_depth1.npz"))
+    cfg = json.loads(str(g["cfg"]))
+    w = build_wrapper(cfg, make_state_dict(json.loads(str(g["shapes"])), seed=31))
+    disc = {"target": "sgm.modules.diffusionmodules.discretizer.LegacyDDPMDiscretization"}
+    den = dn.DiscreteDenoiserWithControl(
+        weighting_config={"target": "sgm.modules.diffusionmodules.denoiser_weighting.EpsWeighting"},
+        scaling_config={"target": "sgm.modules.diffusionmodules.denoiser_scaling.EpsScaling"}, num_idx=1000,
+        discretization_config=disc).cuda()
+    guider = {"target": "sgm.modules.diffusionmodules.guiders.LinearCFG", "params": {"scale": 1.0, "scale_min": 4.0}}
+    opaque = lambda input, sigma, c, control_scale: den(w, input, sigma, c, control_scale)  # noqa: E731
+    fused = sampling.FusedDenoiser(den, w)
+
+    class Noise:
+        def __init__(self):
+            self.n = 0
+
+        def __call__(self, x, **k):
+            self.n += 1
+            return randn(tuple(x.shape), 9000 + self.n).to(x.device, x.dtype)
+
+    def run(make, denoiser, side):
+        smp = make()
+        x = randn((1, 4, side[0], side[1]), 1).cuda()
+        c = {"control": randn((1, 4, side[0], side[1]), 2).cuda(), "crossattn": randn((1, 77, 2048), 3).cuda(), "vector": randn((1, 2816), 4).cuda()}
+        uc = {"control": c["control"], "crossattn": randn((1, 77, 2048), 5).cuda(), "vector": randn((1, 2816), 6).cuda()}
+        monkeypatch.setattr(torch, "randn_like", Noise())
+        return smp(denoiser, x, cond=c, uc=uc, x_center=randn((1, 4, side[0], side[1]), 7).cuda(), control_scale=0.9,
+                   use_linear_control_scale=True, control_scale_start=0.3)
+
+    untiled = lambda: sampling.RestoreEDMSampler(num_steps=3, restore_cfg=4.0, s_churn=5, s_noise=1.01, discretization_config=disc,  # noqa: E731
+                                                 guider_config=guider)
+    tiled = lambda: sampling.TiledRestoreEDMSampler(tile_size=16, tile_stride=8, tile_batch=2, num_steps=3, restore_cfg=4.0, s_churn=5,  # noqa: E731
+                                                    s_noise=1.01, discretization_config=disc, guider_config=guider)
+    for make, side in ((untiled, (24, 16)), (tiled, (32, 24))):
+        a, b = run(make, opaque, side), run(make, fused, side)
+        diff = float((a - b).abs().max())
+        print(f"{'tiled' if make is tiled else 'untiled'}: max |opaque - fused| = {diff:.3g} (max |x| {float(b.abs().max()):.3g})")
+        assert torch.isfinite(a).all() and torch.allclose(a, b, rtol=2e-4, atol=2e-4)
