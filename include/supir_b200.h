@@ -179,6 +179,10 @@ int supir_attention_1head_bf16(const void* q, long long ldq, const void* k, long
  * (0..4; default 0 = all on MUFU, which measured fastest on B200, or the environment variable SUPIR_B200_ATTN_EMU; negative
  * restores the default). */
 int supir_set_attention_exp_emulation(int pairs_of_4);
+/* tuning knob: cycles by which the second query tile of a self-attention CTA starts behind the first, so that the two tiles'
+ * softmax phases interleave on the shared MUFU instead of running in lockstep (environment SUPIR_B200_ATTN_STAGGER; negative
+ * restores the default). */
+int supir_set_attention_stagger(int cycles);
 
 /* ------------------------------------------------------------------------------------------------------------------ */
 /* K7/K8/K10/K12/K14 and data movement (elementwise.cu)                                                               */

@@ -52,6 +52,7 @@ struct AttnParams {
     uint32_t idesc_qk;     // 128 x NKEY, A K-major, B K-major
     uint32_t idesc_pv;     // 128 x 64,  A K-major (TMEM), B MN-major
     int nqb, num_items;    // query blocks per (batch, head); nqb * H * B work items
+    int stagger;           // cycles by which tile B's first QK trails tile A's (see attention_stagger())
 };
 
 // 2^x for a pair, x <= ~100, on the FMA / ALU pipes (no MUFU). x is clamped at -126 (result 2^-126 ~ 0 for anything below,
@@ -243,7 +244,18 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 mbar_wait(&kv_full[0], 0);
                 tc_fence_after();
                 const int nt0 = item_tileB(blockIdx.x) ? 2 : 1;
-                for (int x = 0; x < nt0; ++x) issue_qk(x, 0, 0);
+                issue_qk(0, 0, 0);
+                if (nt0 == 2) {
+                    // Start tile B out of phase with tile A. The two tiles' softmax warps share each sub-partition's MUFU: started
+                    // together they stay in lockstep — both in the exponential phase (each at half rate), then both waiting for
+                    // their next S while the MUFU idles. Offset by part of a softmax period, one tile's wait / load / max phase
+                    // hides behind the other's exponentials, and the offset persists (each tile's blocks chain independently).
+                    if (p.stagger > 0) {
+                        const long long t0 = clock64();
+                        while (clock64() - t0 < p.stagger) {}
+                    }
+                    issue_qk(1, 0, 0);
+                }
             }
             for (int it = blockIdx.x; it < p.num_items; it += gridDim.x, ++k) {
                 const int qi = k & 1;
@@ -409,6 +421,16 @@ static long long g_att_desc_override = -1;
 static long long g_att_idesc_pv_override = -1;
 static int g_att_emu = -1;            // emulated exponent pairs per 4: -1 = environment / default
 
+static int g_att_stagger = -1;        // cycles; -1 = environment / default
+static int attention_stagger() {
+    if (g_att_stagger < 0) {
+        const char* e = getenv("SUPIR_B200_ATTN_STAGGER");
+        g_att_stagger = e ? atoi(e) : 0;
+        if (g_att_stagger < 0) g_att_stagger = 0;
+    }
+    return g_att_stagger;
+}
+
 static int attention_emu() {
     if (g_att_emu < 0) {
         const char* e = getenv("SUPIR_B200_ATTN_EMU");
@@ -437,6 +459,7 @@ static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, cons
     p.nqb = (p.Lq + TILES * ATT_BM - 1) / (TILES * ATT_BM);
     p.num_items = p.nqb * p.H * B;
     p.idesc_qk = umma_idesc_bf16(ATT_BM, NKEY, 0, 0);
+    p.stagger = TILES == 2 ? attention_stagger() : 0;
     const int slots = device_sm_count() * (TILES == 1 ? 2 : 1);
     const int grid = p.num_items < slots ? p.num_items : slots;
     attention_d64_kernel<TILES, STAGES, NKEY, EMU><<<grid, 128 + 128 * TILES, S::TOTAL, st>>>(tmQ, tmK, tmV, p);
@@ -464,6 +487,11 @@ using namespace supir;
 extern "C" int supir_debug_set_attention_descriptors(long long smem_desc_template, long long idesc_pv) {
     g_att_desc_override = smem_desc_template;
     g_att_idesc_pv_override = idesc_pv;
+    return SUPIR_OK;
+}
+
+extern "C" int supir_set_attention_stagger(int cycles) {
+    g_att_stagger = cycles < 0 ? -1 : cycles;
     return SUPIR_OK;
 }
 

@@ -615,6 +615,18 @@ int main(int argc, char** argv) {
         }
         supir_set_gemm_pair_mode(1);
     }
+    if (what == "attnstagger") {   // phase offset between the two query tiles of a self-attention CTA
+        for (int st : {0, 300, 600, 900, 1200, 1600}) {
+            printf("-- tile B starts %d cycles behind tile A\n", st);
+            supir_set_attention_stagger(st);
+            perf_attention(98, 10, 4096, 4096);
+            perf_attention(98, 20, 1024, 1024);
+        }
+        supir_set_attention_stagger(600);
+        test_attention(2, 10, 1024, 1024, 500);
+        test_attention(1, 2, 333, 500, 0);
+        supir_set_attention_stagger(-1);
+    }
     if (what == "epiperf") {     // the step's dominant GEMM shapes (batch 98) under both staged-epilogue modes
         for (int mode : {0, 1}) {
             printf("-- staged epilogue mode %d (%s)\n", mode, mode ? "per-warp TMA, no named barriers" : "one TMA op per 128-row chunk");
