@@ -5,7 +5,8 @@ mkdir -p gpurun_out
 run() { local t=$1 log=$2; shift 2; stdbuf -oL timeout "$t" "$@" > "gpurun_out/$log" 2>&1; local rc=$?; echo "exit=$rc" >> "gpurun_out/$log"; return $rc; }
 run 60 r02_selftest_attnquick3.log tools/selftest attnquick || { tail -n 20 gpurun_out/r02_selftest_attnquick3.log; echo "HANG GUARD FAILED"; exit 1; }
 run 200 r02_pytest_1head.log python -m pytest tests/test_gpu_bench_shapes.py tests/test_gpu_vae_sampler.py -q -m gpu -k "single_head or vae" -s --timeout 120; tail -n 12 gpurun_out/r02_pytest_1head.log
-run 420 r02_bench_cfg3_N1.log python bench.py --steps 10 --warmup 3; tail -n 2 gpurun_out/r02_bench_cfg3_N1.log
+run 120 r02_selftest_attnstagger.log tools/selftest attnstagger; cat gpurun_out/r02_selftest_attnstagger.log
+SUPIR_BENCH_DUMP_SHAPES=gpurun_out/r02_gemm_shapes_B98.json run 420 r02_bench_cfg3_N1.log python bench.py --steps 10 --warmup 3; tail -n 2 gpurun_out/r02_bench_cfg3_N1.log
 run 300 r02_bench_torch_gpu.log python tools/bench_torch_gpu.py 128 2,14,98; tail -n 5 gpurun_out/r02_bench_torch_gpu.log
 run 300 r02_bench_cfg2_N1.log python bench.py --config cfg2 --steps 5 --warmup 3 --no-cpu-baseline; tail -n 2 gpurun_out/r02_bench_cfg2_N1.log
 run 240 r02_bench_cfg5_N1.log python bench.py --config cfg5 --steps 4 --warmup 4 --no-cpu-baseline; tail -n 2 gpurun_out/r02_bench_cfg5_N1.log
