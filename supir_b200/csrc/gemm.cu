@@ -850,9 +850,11 @@ static int run_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmKernelPa
     p.staged = can_stage(p) ? 1 : 0;
     p.has_res = (p.staged && p.residual) ? 1 : 0;
     // per-warp TMA epilogue: +6..21 % on the bias / residual epilogues of the step's GEMMs, -2..5 % on GEGLU (whose chunks are
-    // 16 columns wide: 1 KB per warp and store) — profiles/r02_selftest_epiperf.log. -1 = that rule; 0 / 1 force a mode.
+    // 16 columns wide: 1 KB per warp and store) — profiles/r02_selftest_epiperf.log; convolutions keep the group mode (their
+    // per-warp boxes are 2-4 image-row fragments; the step's convs measured ~10 % slower with them). -1 = that rule; 0 / 1
+    // force a mode.
     const int em = gemm_epilogue_mode();
-    p.warp_epi = (p.staged && (em < 0 ? p.act != 2 : em != 0)) ? 1 : 0;
+    p.warp_epi = (p.staged && (em < 0 ? (p.act != 2 && !p.conv) : em != 0)) ? 1 : 0;
     if (p.staged) {
         const int rc = make_epi_maps(p, &tmC, &tmR);
         if (rc) return rc;
