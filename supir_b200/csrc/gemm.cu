@@ -160,22 +160,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     x0 = (r % p.tiles_x) * p.TW;
                 }
                 const int bn0 = nt * BN + (int)cta_rank * (BN / CTAS);   // first W row of this CTA's share of the B tile
+                // conv mode walks (tap row, tap column, 64-channel chunk) with counters: no division in the per-k-block path
+                // (two runtime divisions per k-block cost the conv kernels 5-13 % when the geometry mode first added them)
+                int cc = 0, tx = 0, ty = 0, wcol = 0;
+                const int ax0 = x0 * p.stride + p.off_x, ay0 = y0 * p.stride + p.off_y;
                 for (int kb = 0; kb < p.num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (CTAS == 1 || cta_rank == 0) mbar_expect_tx(&full_bar[stage], CTAS * S::STAGE_BYTES);
                     uint8_t* sa = smem_a + stage * S::A_BYTES;
                     uint8_t* sb = smem_b + stage * S::B_BYTES;
                     if (p.conv) {
-                        const int tap = kb / p.kchunks;
-                        const int cc = kb - tap * p.kchunks;
-                        const int dy = tap / p.ntaps_x + p.off_y, dx = tap % p.ntaps_x + p.off_x;
-                        const int ax = x0 * p.stride + dx, ay = y0 * p.stride + dy;
+                        const int ax = ax0 + tx, ay = ay0 + ty;
                         if (CTAS == 2) {
                             tma_load_4d_2sm(sa, &tmA, &full_bar[stage], cc * BK, ax, ay, b);
-                            tma_load_2d_2sm(sb, &tmB, &full_bar[stage], tap * p.Cin + cc * BK, bn0);
+                            tma_load_2d_2sm(sb, &tmB, &full_bar[stage], wcol + cc * BK, bn0);
                         } else {
                             tma_load_4d(sa, &tmA, &full_bar[stage], cc * BK, ax, ay, b);
-                            tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.Cin + cc * BK, bn0);
+                            tma_load_2d(sb, &tmB, &full_bar[stage], wcol + cc * BK, bn0);
+                        }
+                        if (++cc == p.kchunks) {                       // next tap: W columns advance by Cin
+                            cc = 0;
+                            wcol += p.Cin;
+                            if (++tx == p.ntaps_x) { tx = 0; ++ty; }
                         }
                     } else {
                         if (CTAS == 2) {
