@@ -71,6 +71,14 @@ class DiscreteDenoiserWithControl(nn.Module):
         idx = int(np.argmin(np.abs(np.float32(sigma) - self._host_table)))
         return float(self._host_table[idx]), idx
 
+    @staticmethod
+    def c_in_host(sigma_q: float) -> float:
+        """EpsScaling's c_in = 1 / (sigma^2 + 1) ** 0.5 evaluated the way torch does on a float32 tensor (pow(x, 0.5) is sqrt):
+        float32 square, add, correctly rounded sqrt, divide (denoiser_scaling.py:16-22). ONE definition, so the fused and the
+        unfused sampler paths feed bit-identical inputs to the network."""
+        s = np.float32(sigma_q)
+        return float(np.float32(1.0) / np.sqrt(s * s + np.float32(1.0)))
+
     # ---- reference-compatible tensor API ----
     def sigma_to_idx(self, sigma):
         dists = sigma - self.sigmas[:, None]
@@ -95,7 +103,7 @@ class DiscreteDenoiserWithControl(nn.Module):
                          control_scale) for i in range(input.shape[0])]
             return torch.cat(outs, 0)
         sq, idx = self.quantize_host(float(sig[0]))
-        c_in = 1.0 / (np.float32(sq) ** 2 + np.float32(1.0)) ** np.float32(0.5)
+        c_in = self.c_in_host(sq)
         x = input.contiguous().float()
         scaled = torch.empty_like(x)
         ops.axpby_f32(x, float(c_in), None, 0.0, scaled)

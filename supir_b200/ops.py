@@ -66,6 +66,16 @@ class Pool:
             base = t if t._base is None else t._base
             self.free.setdefault((base.dtype, base.numel()), []).append(base.view(-1))
 
+    def free_bytes(self):
+        return sum(k[1] * torch.empty((), dtype=k[0]).element_size() * len(v) for k, v in self.free.items())
+
+    def trim(self):
+        """Drop the cached free buffers (they go back to torch's caching allocator); tensors still in use stay with their
+        holders. For pools OUTSIDE a CUDA graph only (the tiled VAE: a 256-tile pass touches four resolutions whose scratch
+        sizes never recur, and keeping all of them cached would not fit 180 GB)."""
+        self.free.clear()
+        self.all = []
+
 
 # ------------------------------------------------------------------------------------------------------------------
 # tensor-core ops

@@ -172,7 +172,7 @@ class RestoreEDMSampler(BaseDiffusionSampler):
         if isinstance(denoiser, FusedDenoiser) and hasattr(self.guider, "scale_host"):
             den = denoiser.denoiser
             sq, idx = den.quantize_host(k["sigma_hat"])
-            c_in = float(f32(1.0) / np.sqrt(f32(sq) * f32(sq) + f32(1.0)))
+            c_in = den.c_in_host(sq)
             x_hat = torch.empty_like(x)
             net_in = torch.empty((2 * N,) + tuple(x.shape[1:]), dtype=torch.float32, device=x.device)
             ops.edm_pre(x, eps if k["gamma"] > 0 else None, k["noise_mul"], c_in, x_hat, net_in)
@@ -259,7 +259,7 @@ class _EDMRun:
         smp, x = self.smp, self.x
         N = x.shape[0]
         sq, idx = self.denoiser.denoiser.quantize_host(k["sigma_hat"])
-        c_in = float(f32(1.0) / np.sqrt(f32(sq) * f32(sq) + f32(1.0)))
+        c_in = self.denoiser.denoiser.c_in_host(sq)
         x_hat = torch.empty_like(x)
         net_in = torch.empty((2 * N,) + tuple(x.shape[1:]), dtype=torch.float32, device=x.device)
         ops.edm_pre(x, eps if k["gamma"] > 0 else None, k["noise_mul"], c_in, x_hat, net_in)
@@ -413,7 +413,7 @@ class _TiledRun:
         nw, n_mine = self.nw, self.n_mine
         den = self.denoiser.denoiser
         sq, idx = den.quantize_host(k["sigma_hat"])
-        c_in = float(f32(1.0) / np.sqrt(f32(sq) * f32(sq) + f32(1.0)))
+        c_in = den.c_in_host(sq)
         x_t = torch.empty((nw, b, ch, T, T), dtype=torch.float32, device=x.device)
         ops.tile_gather(x, self.table_dev, T, x_t)
         e_t = None
@@ -528,7 +528,7 @@ class RestoreDPMPP2MSampler(BaseDiffusionSampler):
         N = x.shape[0]
         if isinstance(denoiser, FusedDenoiser) and hasattr(self.guider, "scale_host"):
             sq, idx = denoiser.denoiser.quantize_host(sigma)
-            c_in = float(f32(1.0) / np.sqrt(f32(sq) * f32(sq) + f32(1.0)))
+            c_in = denoiser.denoiser.c_in_host(sq)
             x_hat = torch.empty_like(x)
             net_in = torch.empty((2 * N,) + tuple(x.shape[1:]), dtype=torch.float32, device=x.device)
             ops.edm_pre(x, None, 0.0, c_in, x_hat, net_in)

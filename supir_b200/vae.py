@@ -22,6 +22,9 @@ from .nets import Act, _bf, _bias_bf16_values, _f32, pack_conv3x3
 from .ops import BF16
 
 
+POOL_TRIM_BYTES = 24 << 30      # cached scratch above this is handed back between resolutions (many-tile images, e.g. 8192^2)
+
+
 def Normalize(in_channels, num_groups=32):
     return nn.GroupNorm(num_groups=num_groups, num_channels=in_channels, eps=1e-6, affine=True)
 
@@ -336,6 +339,8 @@ class _VAENet(nn.Module):
                     dims = [(2 * h, 2 * w) for h, w in dims]
                 elif step[0] == "downsample":
                     dims = [((h + 1 - 3) // 2 + 1, (w + 1 - 3) // 2 + 1) for h, w in dims]
+                if step[0] in ("upsample", "downsample") and pool.free_bytes() > POOL_TRIM_BYTES:
+                    pool.trim()          # scratch of the resolution just left: its sizes do not recur in this pass
                 continue
             # cross-tile GroupNorm: per-tile (mean, biased var) -> pixel-weighted merge -> shared apply
             C = step[3]
@@ -371,6 +376,8 @@ class _VAENet(nn.Module):
                 ob = out_bboxes[i]
                 y0, y1, x0, x1 = crops[i]
                 self._finish_tile(pool, tiles[i], result[:, :, ob[2]:ob[3], ob[0]:ob[1]], crop=(y0, x0, y1 - y0, x1 - x0))
+            if pool.free_bytes() > POOL_TRIM_BYTES:
+                pool.trim()
             return result
         # sharded: every rank packs its cropped tiles back to back; one all-gather; paste
         numel, offs, slot = plan_packed_crops(crops, N * Cout, world)
@@ -381,6 +388,8 @@ class _VAENet(nn.Module):
             self._finish_tile(pool, tiles[i], view, crop=(y0, x0, y1 - y0, x1 - x0))
         dist.all_gather_into_tensor(packed.view(-1), packed[rank].clone(), group=group)
         paste_packed_crops(result, packed, crops, out_bboxes, numel, offs, world)
+        if pool.free_bytes() > POOL_TRIM_BYTES:
+            pool.trim()
         return result
 
 
