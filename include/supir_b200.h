@@ -183,6 +183,10 @@ int supir_set_attention_exp_emulation(int pairs_of_4);
  * softmax phases interleave on the shared MUFU instead of running in lockstep (environment SUPIR_B200_ATTN_STAGGER; negative
  * restores the default). */
 int supir_set_attention_stagger(int cycles);
+/* tuning knob: how many of every 4 probability pairs are rounded / packed to bf16 with integer instructions on the ALU pipe
+ * instead of cvt.rn.bf16x2.f32, which shares the XU pipe with the exponentials (0..4; environment SUPIR_B200_ATTN_ALU_PACK;
+ * negative restores the default). */
+int supir_set_attention_alu_pack(int pairs_of_4);
 
 /* ------------------------------------------------------------------------------------------------------------------ */
 /* K7/K8/K10/K12/K14 and data movement (elementwise.cu)                                                               */

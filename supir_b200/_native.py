@@ -51,6 +51,7 @@ _SIGS = {
     "supir_debug_set_attention_descriptors": [c_ll, c_ll],
     "supir_set_attention_exp_emulation": [c_int],
     "supir_set_attention_stagger": [c_int],
+    "supir_set_attention_alu_pack": [c_int],
     "supir_upsample_nearest2x": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p],
     "supir_im2col_3x3_s2": [c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "supir_copy2d_bf16": [c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p],

@@ -79,9 +79,18 @@ __device__ __forceinline__ void ex2_emulated_pair(uint64_t x, float& e0, float& 
     e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(r1) << 23));
 }
 
+// fp32 pair -> bf16x2 with INTEGER arithmetic: round half up on the magnitude (+0x8000, p >= 0) and take the two high halves
+// with one byte permute. cvt.rn.bf16x2.f32 (F2FP) runs on the same XU pipe as the exponentials — 64 pack instructions
+// per row and block are a fifth of this kernel's XU time — while the ALU pipe these three instructions use is mostly idle.
+// Differs from round-to-nearest-even only on exact ties.
+__device__ __forceinline__ uint32_t pack_bf16x2_alu(float lo, float hi) {
+    return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
+}
+
 // p = 2^(s * scale - m) for NCOL columns of one row (registers s[]), bf16 pairs to TMEM at tP; returns the row sum of p.
-// EMU of every 4 pairs are evaluated by ex2_emulated_pair, the others on MUFU.
-template <int NCOL, int EMU>
+// EMU of every 4 pairs are evaluated by ex2_emulated_pair, the others on MUFU; ICVT of every 4 pairs are packed to bf16 on
+// the ALU pipe (pack_bf16x2_alu), the others by the XU-pipe conversion instruction.
+template <int NCOL, int EMU, int ICVT>
 __device__ __forceinline__ float softmax_row_to_tmem(const uint32_t (&s)[128], float scale_log2, float m_ref, uint32_t tP) {
     const uint64_t sc2 = pack2(scale_log2, scale_log2), nm2 = pack2(-m_ref, -m_ref);
     uint64_t ls[4];
@@ -109,7 +118,8 @@ __device__ __forceinline__ float softmax_row_to_tmem(const uint32_t (&s)[128], f
                         e1 = ex2_approx(x1);
                     }
                     ls[t] = fadd2(ls[t], pack2(e0, e1));
-                    pk[(i >> 1) + t] = pack_bf16x2(e0, e1);
+                    const bool alu_pack = (ICVT == 4) || (ICVT == 2 && !(t & 1)) || (ICVT == 1 && t == 0) || (ICVT == 3 && t != 2);
+                    pk[(i >> 1) + t] = alu_pack ? pack_bf16x2_alu(e0, e1) : pack_bf16x2(e0, e1);
                 } else {
                     pk[(i >> 1) + t] = 0u;
                 }
@@ -137,7 +147,7 @@ struct AttnSmem {
     static constexpr int TOTAL = OFF_BAR + 256 + 1024;
 };
 
-template <int TILES, int STAGES, int NKEY, int EMU>
+template <int TILES, int STAGES, int NKEY, int EMU, int ICVT>
 __global__ void __launch_bounds__(128 + 128 * TILES, TILES == 1 ? 2 : 1)
 attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -376,7 +386,7 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                         tmem_st_wait();
                     }
                 }
-                l_run += softmax_row_to_tmem<NKEY, EMU>(s, p.scale_log2, m_ref, tP);
+                l_run += softmax_row_to_tmem<NKEY, EMU, ICVT>(s, p.scale_log2, m_ref, tP);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&p_full[x]);
@@ -431,6 +441,16 @@ static int attention_stagger() {
     return g_att_stagger;
 }
 
+static int g_att_icvt = -1;           // pairs of every 4 packed to bf16 on the ALU pipe: -1 = environment / default
+static int attention_int_pack() {
+    if (g_att_icvt < 0) {
+        const char* e = getenv("SUPIR_B200_ATTN_ALU_PACK");
+        g_att_icvt = e ? atoi(e) : 4;
+        if (g_att_icvt < 0 || g_att_icvt > 4) g_att_icvt = 4;
+    }
+    return g_att_icvt;
+}
+
 static int attention_emu() {
     if (g_att_emu < 0) {
         const char* e = getenv("SUPIR_B200_ATTN_EMU");
@@ -443,7 +463,7 @@ static int attention_emu() {
     return g_att_emu;
 }
 
-template <int TILES, int STAGES, int NKEY, int EMU>
+template <int TILES, int STAGES, int NKEY, int EMU, int ICVT>
 static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, AttnParams p, int B,
                             cudaStream_t st) {
     using S = AttnSmem<TILES, STAGES>;
@@ -452,7 +472,7 @@ static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, cons
     int dev = 0;
     SUPIR_CHECK_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        SUPIR_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<TILES, STAGES, NKEY, EMU>,
+        SUPIR_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<TILES, STAGES, NKEY, EMU, ICVT>,
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
@@ -462,7 +482,7 @@ static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, cons
     p.stagger = TILES == 2 ? attention_stagger() : 0;
     const int slots = device_sm_count() * (TILES == 1 ? 2 : 1);
     const int grid = p.num_items < slots ? p.num_items : slots;
-    attention_d64_kernel<TILES, STAGES, NKEY, EMU><<<grid, 128 + 128 * TILES, S::TOTAL, st>>>(tmQ, tmK, tmV, p);
+    attention_d64_kernel<TILES, STAGES, NKEY, EMU, ICVT><<<grid, 128 + 128 * TILES, S::TOTAL, st>>>(tmQ, tmK, tmV, p);
     count_launch();
     SUPIR_CHECK_CUDA(cudaGetLastError());
     return SUPIR_OK;
@@ -471,12 +491,15 @@ static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, cons
 template <int TILES, int STAGES, int NKEY>
 static int launch_attention_emu(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnParams& p, int B,
                                 cudaStream_t st) {
-    switch (attention_emu()) {
-        case 1: return launch_attention<TILES, STAGES, NKEY, 1>(tmQ, tmK, tmV, p, B, st);
-        case 3: return launch_attention<TILES, STAGES, NKEY, 3>(tmQ, tmK, tmV, p, B, st);
-        case 4: return launch_attention<TILES, STAGES, NKEY, 4>(tmQ, tmK, tmV, p, B, st);
-        case 2: return launch_attention<TILES, STAGES, NKEY, 2>(tmQ, tmK, tmV, p, B, st);
-        default: return launch_attention<TILES, STAGES, NKEY, 0>(tmQ, tmK, tmV, p, B, st);
+    const int emu = attention_emu(), icvt = attention_int_pack();
+    if (emu >= 2) {      // the (measured slower) exponent emulation keeps one instantiation for the record
+        return launch_attention<TILES, STAGES, NKEY, 2, 0>(tmQ, tmK, tmV, p, B, st);
+    }
+    switch (icvt) {
+        case 0: return launch_attention<TILES, STAGES, NKEY, 0, 0>(tmQ, tmK, tmV, p, B, st);
+        case 1: case 2: return launch_attention<TILES, STAGES, NKEY, 0, 2>(tmQ, tmK, tmV, p, B, st);
+        case 3: return launch_attention<TILES, STAGES, NKEY, 0, 3>(tmQ, tmK, tmV, p, B, st);
+        default: return launch_attention<TILES, STAGES, NKEY, 0, 4>(tmQ, tmK, tmV, p, B, st);
     }
 }
 
@@ -487,6 +510,11 @@ using namespace supir;
 extern "C" int supir_debug_set_attention_descriptors(long long smem_desc_template, long long idesc_pv) {
     g_att_desc_override = smem_desc_template;
     g_att_idesc_pv_override = idesc_pv;
+    return SUPIR_OK;
+}
+
+extern "C" int supir_set_attention_alu_pack(int pairs_of_4) {
+    g_att_icvt = pairs_of_4 < 0 ? -1 : (pairs_of_4 > 4 ? 4 : pairs_of_4);
     return SUPIR_OK;
 }
 
@@ -753,7 +781,7 @@ attention_d512_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 }
             }
             // P(j) overwrites the first 64 columns of S[buf]: its previous reader, PV(j-2), retired before QK(j) could run
-            l_run += softmax_row_to_tmem<ATT_BN, EMU>(s, p.scale_log2, m_ref, tS);
+            l_run += softmax_row_to_tmem<ATT_BN, EMU, 0>(s, p.scale_log2, m_ref, tS);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[buf]);

@@ -197,29 +197,39 @@ ATT_SHAPES = [(98, 10, 4096, 4096), (98, 20, 1024, 1024), (98, 10, 4096, 77), (9
               (3, 5, 1000, 500), (2, 10, 1300, 640), (4, 3, 333, 96), (3, 2, 260, 128), (2, 20, 1024, 1024)]
 
 
-@pytest.mark.parametrize("emu", [0, 2, 4])
+# softmax variants: (exponent pairs of 4 emulated on the FMA pipe, probability pairs of 4 packed to bf16 on the ALU pipe)
+ATT_MODES = {"default": (-1, -1), "xu_pack": (0, 0), "half_alu_pack": (0, 2), "alu_pack": (0, 4), "exp_emulation": (2, 0)}
+
+
+def _set_attention_mode(lib, mode):
+    emu, pack = ATT_MODES[mode]
+    lib.supir_set_attention_exp_emulation(emu)
+    lib.supir_set_attention_alu_pack(pack)
+
+
+@pytest.mark.parametrize("mode", list(ATT_MODES))
 @pytest.mark.parametrize("shape", ATT_SHAPES, ids=lambda s: "B%d_H%d_Lq%d_Lk%d" % s)
-def test_attention_bench_shapes(shape, emu):
+def test_attention_bench_shapes(shape, mode):
     ops, native = _ops()
     B, H, Lq, Lk = shape
-    if emu != 2 and B * H * Lq * Lk > 2e9:
-        pytest.skip("the largest shapes run once, with the default exponent emulation")
+    if mode != "default" and B * H * Lq * Lk > 2e9:
+        pytest.skip("the largest shapes run once, in the default mode")
     C = H * 64
     q, k, v = _rand((B * Lq, C), 31, 1.5), _rand((B * Lk, C), 32, 1.5), _rand((B * Lk, C), 33)
     ref = _ref_attention(q, k, v, B, H, Lq, Lk, 0.125)
     lib = native.load()
     try:
-        lib.supir_set_attention_exp_emulation(emu)
+        _set_attention_mode(lib, mode)
         out = torch.full((B * Lq, C), float("nan"), dtype=BF, device="cuda")
         ops.attention(q, k, v, out, B, H, Lq, Lk)
-        _check_attention(out, ref, f"attention {shape} emu={emu}")
+        _check_attention(out, ref, f"attention {shape} {mode}")
     finally:
-        lib.supir_set_attention_exp_emulation(-1)
+        _set_attention_mode(lib, "default")
 
 
-@pytest.mark.parametrize("emu", [0, 2, 4])
+@pytest.mark.parametrize("mode", ["default", "xu_pack", "exp_emulation"])
 @pytest.mark.parametrize("Lk", [1024, 4096, 640])
-def test_attention_adversarial_logits_force_rescale(Lk, emu):
+def test_attention_adversarial_logits_force_rescale(Lk, mode):
     """Key block j is aligned with the queries with a gain that grows with j, so the row maximum rises by ~9 log2 units
     (> the lazy-rescale threshold of 8) in EVERY 128-key block for the even query rows, while the odd rows keep their first
     maximum (both branches inside one warp); a few rows are all-equal (q = 0 -> uniform average of V)."""
@@ -244,17 +254,17 @@ def test_attention_adversarial_logits_force_rescale(Lk, emu):
     ref = _ref_attention(qb, kb, vb, B, H, Lq, Lk, 0.125)
     lib = native.load()
     try:
-        lib.supir_set_attention_exp_emulation(emu)
+        _set_attention_mode(lib, mode)
         out = torch.full((B * Lq, C), float("nan"), dtype=BF, device="cuda")
         ops.attention(qb, kb, vb, out, B, H, Lq, Lk)
-        _check_attention(out, ref, f"adversarial attention Lk={Lk} emu={emu}")
+        _check_attention(out, ref, f"adversarial attention Lk={Lk} {mode}")
         # descending gain: the maximum sits in the first block and later blocks underflow towards zero probability
         kd = (k - u * (blocks * 6.3 / (8.0 * 0.125)) * 2).reshape(B * Lk, C).to(BF).contiguous()
         ref_d = _ref_attention(qb, kd, vb, B, H, Lq, Lk, 0.125)
         ops.attention(qb, kd, vb, out, B, H, Lq, Lk)
-        _check_attention(out, ref_d, f"descending-logit attention Lk={Lk} emu={emu}")
+        _check_attention(out, ref_d, f"descending-logit attention Lk={Lk} {mode}")
     finally:
-        lib.supir_set_attention_exp_emulation(-1)
+        _set_attention_mode(lib, "default")
 
 
 @pytest.mark.parametrize("B,L,D", [(1, 18496, 512), (1, 22500, 512), (2, 300, 512), (1, 128, 512), (2, 777, 256), (3, 200, 128), (1, 4096, 128)])
