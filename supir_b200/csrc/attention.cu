@@ -445,8 +445,8 @@ static int g_att_icvt = -1;           // pairs of every 4 packed to bf16 on the 
 static int attention_int_pack() {
     if (g_att_icvt < 0) {
         const char* e = getenv("SUPIR_B200_ATTN_ALU_PACK");
-        g_att_icvt = e ? atoi(e) : 4;
-        if (g_att_icvt < 0 || g_att_icvt > 4) g_att_icvt = 4;
+        g_att_icvt = e ? atoi(e) : 0;
+        if (g_att_icvt < 0 || g_att_icvt > 4) g_att_icvt = 0;
     }
     return g_att_icvt;
 }
