@@ -331,7 +331,23 @@ class _VAENet(nn.Module):
         tiles = {i: self._start_tile(pool, z[:, :, in_bboxes[i][2]:in_bboxes[i][3], in_bboxes[i][0]:in_bboxes[i][1]]) for i in mine}
         # spatial size of EVERY tile at the current depth (host integers; every rank needs all pixel counts for the merge)
         dims = [(b[3] - b[2], b[1] - b[0]) for b in in_bboxes]
-        for step, fuse in self._fused_steps():
+        # pixel-count weights of the cross-tile merge for EVERY GroupNorm layer, from host integers, uploaded ONCE: a
+        # host -> device copy inside the layer loop drains the launch queue at each of the ~26 layers (at 2 tiles per rank the
+        # pass was CPU-bound on exactly that: 289 ms for 4 passes on 8 GPUs against ~100 ms of kernels)
+        plan_steps = self._fused_steps()
+        wrows, d2 = [], list(dims)
+        for step, _ in plan_steps:
+            if step[0] == "upsample":
+                d2 = [(2 * h, 2 * w) for h, w in d2]
+            elif step[0] == "downsample":
+                d2 = [((h + 1 - 3) // 2 + 1, (w + 1 - 3) // 2 + 1) for h, w in d2]
+            elif step[0] == "norm":
+                pixels = torch.tensor([float(h * w) for h, w in d2], dtype=torch.float32)
+                wts = pixels / pixels.max()
+                wrows.append(wts / wts.sum())            # GroupNormParam.summary (tilevae.py:629-648)
+        wts_all = torch.stack(wrows, 0).to(dev, non_blocking=True) if wrows else None
+        norm_idx = 0
+        for step, fuse in plan_steps:
             if step[0] != "norm":
                 for i in mine:
                     self._apply_step(pool, step, tiles[i], fuse)
@@ -346,7 +362,6 @@ class _VAENet(nn.Module):
             C = step[3]
             n = N * 32
             stats = torch.zeros((per, 2, n), dtype=torch.float32, device=dev)      # this rank's tiles, slot-major
-            pixels = torch.tensor([float(h * w) for h, w in dims], dtype=torch.float32)
             for i in mine:
                 a = tiles[i]["h"]
                 ws = pool.get((ops.groupnorm_ws_size(a.B, a.HW, a.C),), torch.float64)
@@ -358,8 +373,8 @@ class _VAENet(nn.Module):
                 dist.all_gather_into_tensor(allst.view(-1), stats.view(-1), group=group)
                 stats = allst.transpose(0, 1).reshape(per * world, 2, n)            # row slot * world + rank == tile index
             t_mean, t_var = stats[:T, 0].contiguous(), stats[:T, 1].contiguous()
-            wts = pixels / pixels.max()
-            wts = (wts / wts.sum()).to(dev)      # GroupNormParam.summary (tilevae.py:629-648)
+            wts = wts_all[norm_idx]
+            norm_idx += 1
             mean = torch.empty(n, dtype=torch.float32, device=dev)
             var = torch.empty(n, dtype=torch.float32, device=dev)
             ops.groupnorm_merge_tiles(t_mean, t_var, wts, mean, var)
