@@ -10,28 +10,30 @@ from ._native import call
 from .ops import _need_cuda, _ptr, _stream
 
 
-def PIL2Tensor(img, upsacle=1, min_size=1024, fix_resize=None):
-    """PIL.Image -> Tensor[C, H, W], RGB, [-1, 1] (SUPIR/util.py:60-84; argument names as in the reference)."""
-    from PIL import Image
-    w, h = img.size
-    w *= upsacle
-    h *= upsacle
-    w0, h0 = round(w), round(h)
-    if min(w, h) < min_size:
-        _upsacle = min_size / min(w, h)
-        w *= _upsacle
-        h *= _upsacle
+def _target_size(size, upscale, min_size, fix_resize):
+    """Working size (multiples of 64) and requested output size of PIL2Tensor, with the reference's float operation order
+    (SUPIR/util.py:65-79): scale, report the rounded size, grow the short side to `min_size`, optionally pin the short side to
+    `fix_resize` (which also redefines the reported size), snap to 64."""
+    dims = [float(size[0]) * upscale, float(size[1]) * upscale]          # (w, h)
+    report = tuple(round(d) for d in dims)
+    short = min(dims)
+    if short < min_size:
+        grow = min_size / short
+        dims = [d * grow for d in dims]
     if fix_resize is not None:
-        _upsacle = fix_resize / min(w, h)
-        w *= _upsacle
-        h *= _upsacle
-        w0, h0 = round(w), round(h)
-    w = int(np.round(w / 64.0)) * 64
-    h = int(np.round(h / 64.0)) * 64
-    x = img.resize((w, h), Image.BICUBIC)
-    x = np.array(x).round().clip(0, 255).astype(np.uint8)
-    x = x / 255 * 2 - 1
-    x = torch.tensor(x, dtype=torch.float32).permute(2, 0, 1)
+        pin = fix_resize / min(dims)
+        dims = [d * pin for d in dims]
+        report = tuple(round(d) for d in dims)
+    work = tuple(int(np.round(d / 64.0)) * 64 for d in dims)
+    return work, report
+
+
+def PIL2Tensor(img, upsacle=1, min_size=1024, fix_resize=None):
+    """PIL.Image -> (Tensor[C, H, W] RGB in [-1, 1], h0, w0) — SUPIR/util.py:60-84 (the keyword `upsacle` is the reference's)."""
+    from PIL import Image
+    (w, h), (w0, h0) = _target_size(img.size, upsacle, min_size, fix_resize)
+    pixels = np.array(img.resize((w, h), Image.BICUBIC)).round().clip(0, 255).astype(np.uint8)
+    x = torch.tensor(pixels / 255 * 2 - 1, dtype=torch.float32).permute(2, 0, 1)
     return x, h0, w0
 
 
