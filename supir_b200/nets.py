@@ -596,7 +596,13 @@ class _UNetBase(nn.Module):
         # emb = time_embed(t) + label_emb(y) is only consumed through the ResBlocks' SiLU -> Linear: store SiLU(emb) once
         ops.linear_small_m(h2, self._le[2], self._le[3], emb, add=e_t, silu_out=2)
         ctx.emb_all = p.get((B, self._emb_w.shape[0]), torch.float32)
-        ops.linear_small_m(emb, self._emb_w, self._emb_b, ctx.emb_all)
+        if B > 16:      # every ResBlock's emb projection at once: [B, 1280] x [sum Cout, 1280]^T — a tensor-core GEMM beyond a few rows
+            emb_bf = p.get((B, emb.shape[1]))
+            ops.f32_to_bf16(emb, emb_bf)
+            ops.gemm(emb_bf, self._emb_w, ctx.emb_all, bias=self._emb_b)
+            p.put(emb_bf)
+        else:
+            ops.linear_small_m(emb, self._emb_w, self._emb_b, ctx.emb_all)
         p.put(temb, h1, e_t, h2, emb)
         ctx.kv_owned = ctx_kv is None
         if ctx_kv is None:
