@@ -22,7 +22,10 @@ from .nets import Act, _bf, _bias_bf16_values, _f32, pack_conv3x3
 from .ops import BF16
 
 
-POOL_TRIM_BYTES = 24 << 30      # cached scratch above this is handed back between resolutions (many-tile images, e.g. 8192^2)
+# cached scratch above this is handed back to torch's allocator between resolutions (many-tile images: an 8192^2 pass would
+# otherwise keep ~170 GB of four resolutions' buffers cached). High enough that the 4096^2 workload (26 GB) never trims:
+# re-acquiring trimmed buffers costs cudaMalloc time (a ~1 s spike was measured in one bench run with a 24 GB threshold).
+POOL_TRIM_BYTES = 64 << 30
 
 
 def Normalize(in_channels, num_groups=32):
