@@ -241,6 +241,29 @@ int supir_gaussian_latent(const float* moments, const float* eps, float scale, f
                           void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------ */
+/* text conditioner (textenc.cu): CLIP-L and OpenCLIP bigG text towers, once per image          */
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* out[r, 0:C] = table[idx[r], 0:C] (+ pos[r % L, 0:C] when pos != NULL), fp32; idx int32, clamped to [0, table_rows).
+ * Replaces the nn.Embedding lookups + positional add of the text towers (HF CLIPTextEmbeddings behind
+ * sgm/modules/encoders/modules.py:494-496; open_clip token_embedding + positional_embedding, modules.py:569-570) and the
+ * EOT-row gather of `pool` (modules.py:584-590: x[arange, text.argmax(-1)]). */
+int supir_gather_rows_f32(const float* table, long long ldt, int table_rows, const int* idx, const float* pos, long long ldp,
+                          int L, float* out, long long ldo, long long rows, int C, void* stream);
+/* nn.LayerNorm over fp32 rows (the towers keep their residual stream in fp32: autocast lowers only the matmuls), written as
+ * bf16 (y_bf16, the next GEMM's operand) and / or fp32 (y_f32: ln_final, modules.py:574,580); either may be NULL.
+ * Replaces layer_norm1/2 + final_layer_norm of HF CLIPEncoderLayer and ln_1 / ln_2 / ln_final of open_clip's resblocks. */
+int supir_layernorm_f32(const float* x, long long ldx, void* y_bf16, long long ldyb, float* y_f32, long long ldyf, long long rows,
+                        int C, const float* gamma, const float* beta, float eps, void* stream);
+/* softmax(q k^T * scale [+ causal mask]) v for short sequences: L <= 128 tokens, head_dim 64; q/k/v/out bf16 [B*L, ld], head h at
+ * column h*64. Replaces the text towers' masked self-attention (HF CLIPAttention with the causal mask; open_clip
+ * nn.MultiheadAttention(attn_mask=model.attn_mask), modules.py:571,592-607). */
+int supir_attention_small_bf16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
+                               long long ldo, int B, int H, int L, int head_dim, float scale, int causal, void* stream);
+/* y = act(x) on bf16 rows (x, y may alias): mode 0 exact GELU (open_clip nn.GELU), mode 1 quick-GELU x * sigmoid(1.702 x)
+ * (openai/clip-vit-large-patch14 `hidden_act`). */
+int supir_activation_bf16(const void* x, long long ldx, void* y, long long ldy, long long rows, int cols, int mode, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------ */
 /* colour fix on the decoded image (colorfix.cu; SUPIR/utils/colorfix.py)                     */
 /* ------------------------------------------------------------------------------------------------------------------ */
 /* one a-trous wavelet level on fp32 NCHW planes: low = blur(img) with the 3x3 kernel [1 2 1]x[1 2 1]/16 at dilation

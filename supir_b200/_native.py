@@ -72,6 +72,10 @@ _SIGS = {
     "supir_plane_stats": [c_void_p, c_int, c_ll, c_void_p, c_ll, c_void_p],
     "supir_adain_apply": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_void_p],
     "supir_image_to_uint8_bicubic": [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p],
+    "supir_gather_rows_f32": [c_void_p, c_ll, c_int, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_ll, c_ll, c_int, c_void_p],
+    "supir_layernorm_f32": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p, c_void_p, c_float, c_void_p],
+    "supir_attention_small_bf16": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p],
+    "supir_activation_bf16": [c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_int, c_void_p],
     "supir_gaussian_latent": [c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_ll, c_void_p],
 }
 _SPECIAL = {

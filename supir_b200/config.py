@@ -25,6 +25,13 @@ _ALIASES = {
     "SUPIR.modules.SUPIR_v0.LightGLVUNet": "supir_b200.nets.LightGLVUNet",
     "sgm.models.autoencoder.AutoencoderKLInferenceWrapper": "supir_b200.vae.AutoencoderKLInferenceWrapper",
     "sgm.models.autoencoder.AutoencoderKL": "supir_b200.vae.AutoencoderKL",
+    "sgm.modules.GeneralConditioner": "supir_b200.conditioner.GeneralConditioner",
+    "sgm.modules.GeneralConditionerWithControl": "supir_b200.conditioner.GeneralConditionerWithControl",
+    "sgm.modules.encoders.modules.GeneralConditioner": "supir_b200.conditioner.GeneralConditioner",
+    "sgm.modules.encoders.modules.GeneralConditionerWithControl": "supir_b200.conditioner.GeneralConditionerWithControl",
+    "sgm.modules.encoders.modules.FrozenCLIPEmbedder": "supir_b200.conditioner.FrozenCLIPEmbedder",
+    "sgm.modules.encoders.modules.FrozenOpenCLIPEmbedder2": "supir_b200.conditioner.FrozenOpenCLIPEmbedder2",
+    "sgm.modules.encoders.modules.ConcatTimestepEmbedderND": "supir_b200.conditioner.ConcatTimestepEmbedderND",
 }
 
 

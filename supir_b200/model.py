@@ -4,8 +4,8 @@ sgm/models/diffusion.py:22-83).
 The reference keeps this layer as Python orchestration (stage-1 encode/decode, conditioning, sampler call, decode); it is
 the CALLER of the hot path. This class offers the same constructor keys (so `options/SUPIR_v0*.yaml` instantiates it
 through supir_b200.config) and the same methods, wired to this package's networks, samplers and VAE. The text conditioner
-(CLIP encoders) is outside the hot path: pass `conditioner_config=None` and hand `c` / `uc`
-dictionaries to `batchify_sample`, or install the reference's `sgm` package for it.
+ resolves to supir_b200.conditioner (kernel-backed CLIP-L / bigG text towers with the reference's state_dict
+keys); without a CLIP BPE vocabulary on disk, hand token ids to the embedders or `c` / `uc` dictionaries to `batchify_sample`.
 """
 import copy
 import random
@@ -112,8 +112,8 @@ class SUPIRModel(nn.Module):
 
     def prepare_condition(self, _z, p, p_p, n_p, N):
         if self.conditioner is None:
-            raise RuntimeError("no text conditioner is attached (it is outside the accelerated hot path): "
-                               "pass c= and uc= to batchify_sample, or install the reference's sgm package")
+            raise RuntimeError("no text conditioner is attached (conditioner_config was None or failed to build: "
+                               f"{getattr(self, '_conditioner_error', None)!r}): pass c= and uc= to batchify_sample")
         batch = {"original_size_as_tuple": torch.tensor([1024, 1024]).repeat(N, 1).to(_z.device),
                  "crop_coords_top_left": torch.tensor([0, 0]).repeat(N, 1).to(_z.device),
                  "target_size_as_tuple": torch.tensor([1024, 1024]).repeat(N, 1).to(_z.device),

@@ -411,6 +411,53 @@ def linear_small_m(x, w, bias, out, silu_in=False, silu_out=False, add=None):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# text conditioner (textenc.cu)
+# ------------------------------------------------------------------------------------------------------------------
+def gather_rows_f32(table, idx, out, pos=None, L=0):
+    """out[r] = table[idx[r]] (+ pos[r % L]); table / pos / out fp32 matrices, idx int32 [rows]."""
+    _need_cuda(table, idx, out, pos)
+    assert table.dtype == torch.float32 and out.dtype == torch.float32 and idx.dtype == torch.int32 and idx.is_contiguous()
+    assert table.dim() == 2 and out.dim() == 2 and table.stride(1) == 1 and out.stride(1) == 1 and out.shape == (idx.numel(), table.shape[1])
+    assert pos is None or (pos.dtype == torch.float32 and pos.stride(1) == 1 and pos.shape[1] == table.shape[1] and pos.shape[0] >= L > 0)
+    call("supir_gather_rows_f32", _ptr(table), table.stride(0), table.shape[0], _ptr(idx), _ptr(pos), 0 if pos is None else pos.stride(0),
+         int(L), _ptr(out), out.stride(0), out.shape[0], table.shape[1], _stream())
+    return out
+
+
+def layernorm_f32(x, gamma, beta, eps=1e-5, out_bf16=None, out_f32=None):
+    """LayerNorm of fp32 rows x [rows, C] into a bf16 and / or an fp32 matrix."""
+    _need_cuda(x, out_bf16, out_f32)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1 and (out_bf16 is not None or out_f32 is not None)
+    assert out_bf16 is None or (_mat(out_bf16).shape == x.shape)
+    assert out_f32 is None or (_mat(out_f32, torch.float32).shape == x.shape)
+    call("supir_layernorm_f32", _ptr(x), x.stride(0), _ptr(out_bf16), 0 if out_bf16 is None else out_bf16.stride(0), _ptr(out_f32),
+         0 if out_f32 is None else out_f32.stride(0), x.shape[0], x.shape[1], _ptr(gamma), _ptr(beta), float(eps), _stream())
+    return out_bf16 if out_bf16 is not None else out_f32
+
+
+def attention_small(q, k, v, out, B, heads, L, causal=True, scale=None):
+    """Short-sequence (L <= 128) attention with head_dim 64 and an optional causal mask; q/k/v/out bf16 [B*L, >= heads*64]."""
+    _need_cuda(q, k, v, out)
+    for t in (q, k, v, out):
+        _mat(t)
+        assert t.shape[0] == B * L
+    d = q.shape[1] // heads
+    call("supir_attention_small_bf16", _ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out), out.stride(0),
+         B, heads, L, d, float(scale if scale is not None else d ** -0.5), int(bool(causal)), _stream())
+    return out
+
+
+def activation(x, out, mode):
+    """out = GELU(x) (mode 'gelu', exact erf form) or x * sigmoid(1.702 x) (mode 'quick_gelu'); bf16, x and out may alias."""
+    _need_cuda(x, out)
+    _mat(x), _mat(out)
+    assert x.shape == out.shape
+    call("supir_activation_bf16", _ptr(x), x.stride(0), _ptr(out), out.stride(0), x.shape[0], x.shape[1],
+         {"gelu": 0, "quick_gelu": 1}[mode], _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # sampler
 # ------------------------------------------------------------------------------------------------------------------
 def edm_pre(x, eps, noise_mul, c_in, x_hat, net_in):

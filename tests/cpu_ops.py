@@ -249,6 +249,38 @@ def gaussian_latent(moments, eps, scale, z):
     return z
 
 
+# ---- text conditioner ----
+def gather_rows_f32(table, idx, out, pos=None, L=0):
+    v = table[idx.long().clamp(0, table.shape[0] - 1)]
+    if pos is not None:
+        v = v + pos[torch.arange(idx.numel()) % L]
+    out.copy_(v)
+    return out
+
+
+def layernorm_f32(x, gamma, beta, eps=1e-5, out_bf16=None, out_f32=None):
+    y = F.layer_norm(x.float(), (x.shape[1],), gamma.float(), beta.float(), eps)
+    if out_bf16 is not None:
+        out_bf16.copy_(y.to(BF))
+    if out_f32 is not None:
+        out_f32.copy_(y)
+    return out_bf16 if out_bf16 is not None else out_f32
+
+
+def attention_small(q, k, v, out, B, heads, L, causal=True, scale=None):
+    d = q.shape[1] // heads
+    sp = lambda t: t.float().reshape(B, L, heads, d).transpose(1, 2)  # noqa: E731
+    o = F.scaled_dot_product_attention(sp(q), sp(k), sp(v), is_causal=bool(causal), scale=scale)
+    out.copy_(o.transpose(1, 2).reshape(B * L, heads * d).to(out.dtype))
+    return out
+
+
+def activation(x, out, mode):
+    xf = x.float()
+    out.copy_((_gelu(xf) if mode == "gelu" else xf * torch.sigmoid(1.702 * xf)).to(out.dtype))
+    return out
+
+
 # ---- sampler ----
 def tile_gather(src, windows, tile, out):
     for j, (hi, he, wi, we) in enumerate(windows.tolist()):
@@ -303,7 +335,8 @@ def cfg_combine(x, scale, out):
 _ALL = ["gemm", "conv3x3", "conv_geom", "attention", "attention_1head", "groupnorm_ws_size", "groupnorm_stats", "groupnorm_finalize",
         "groupnorm_merge_tiles", "groupnorm_apply", "zerosft_apply", "layernorm", "layernorm_stats", "conv3x3_small_cin",
         "conv3x3_small_cout", "conv1x1_small_nchw", "timestep_embedding", "linear_small_m", "upsample2x", "im2col_s2", "f32_to_bf16", "copy2d", "axpy",
-        "gaussian_latent", "tile_gather", "tile_blend", "edm_pre", "edm_post", "axpby_f32", "cfg_combine"]
+        "gaussian_latent", "tile_gather", "tile_blend", "edm_pre", "edm_post", "axpby_f32", "cfg_combine",
+        "gather_rows_f32", "layernorm_f32", "attention_small", "activation"]
 
 
 def install(monkeypatch_or_none=None):

@@ -28,6 +28,7 @@ def regen(tmp_path_factory):
         mg.gen_glvcontrol_tiny()
         mg.gen_sampler()
         mg.gen_colorfix()
+        mg.gen_conditioner()
     finally:
         mg.HERE = saved
     return str(out)
@@ -48,7 +49,7 @@ def test_bookkeeping_and_weights_regenerate_bit_identically(regen):
     _same_npz(os.path.join(regen, "gaussian_weights.npz"), os.path.join(G, "gaussian_weights.npz"))
 
 
-@pytest.mark.parametrize("name", ["zero_modules.npz", "glvcontrol_tiny.npz", "sampler_toy.npz", "colorfix.npz"])
+@pytest.mark.parametrize("name", ["zero_modules.npz", "glvcontrol_tiny.npz", "sampler_toy.npz", "colorfix.npz", "conditioner.npz"])
 def test_tensor_fixtures_regenerate_bit_identically(regen, name):
     _same_npz(os.path.join(regen, name), os.path.join(G, name))
 
