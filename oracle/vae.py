@@ -167,16 +167,60 @@ def _custom_group_norm(t, mean, var, weight, bias, eps=1e-6):
     return out * weight.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
 
 
-def tiled_forward(sd, prefix, z, tile_size, is_decoder):
-    """VAEHook.vae_tile_forward with fast_mode=False (tilevae.py:819-970)."""
+def fast_mode_thumbnail(z, tile_size):
+    """vae_tile_forward, fast mode (tilevae.py:855-873): nearest-exact downsample of the whole input to about one tile, its
+    per-channel mean / std restored to the full input's, clamped to the input's range."""
+    scale_factor = tile_size / max(z.shape[2], z.shape[3])
+    d = F.interpolate(z, scale_factor=scale_factor, mode="nearest-exact")
+    std_old, mean_old = torch.std_mean(z, dim=[0, 2, 3], keepdim=True)
+    std_new, mean_new = torch.std_mean(d, dim=[0, 2, 3], keepdim=True)
+    d = (d - mean_new) / std_new * std_old + mean_old
+    return torch.clamp_(d, min=z.min(), max=z.max())
+
+
+def estimate_group_norm(sd, steps, x, color_fix=False):
+    """estimate_group_norm (tilevae.py:776-817): run the layers on the thumbnail as ONE tile and keep the (var, mean) each
+    GroupNorm sees there (GroupNormParam.from_tile); with color_fix only the layers before the first downsample are estimated.
+    Returns one (var, mean) or None per 'norm' step."""
+    res, fixed = [], []
+    n_norm = sum(1 for s_ in steps if s_[0] == "norm")
+    for step in steps:
+        if step[0] == "norm":
+            var, mean = _var_mean(x)
+            fixed.append((var, mean))
+            if len(fixed) == n_norm:
+                break
+            x = _custom_group_norm(x, mean, var, sd[step[1] + ".weight"], sd[step[1] + ".bias"])
+        elif step[0] == "store_res":
+            res.append(x if step[1] is None else _conv(sd, step[1], x, padding=0))
+        elif step[0] == "add_res":
+            x = x + res.pop()
+        elif color_fix and step[0] == "downsample":
+            break
+        else:
+            x = _apply_plain(sd, step, x)
+    return fixed + [None] * (n_norm - len(fixed))
+
+
+def tiled_forward(sd, prefix, z, tile_size, is_decoder, fast=False, color_fix=False):
+    """VAEHook.vae_tile_forward (tilevae.py:819-970); fast=True is its fast mode (statistics from estimate_group_norm, no
+    cross-tile merge for the estimated layers)."""
     n, _, height, width = z.shape
     if not needs_tiling(height, width, tile_size, is_decoder):
         return forward(sd, prefix, z, is_decoder)
     in_bboxes, out_bboxes = split_tiles(height, width, tile_size, is_decoder)
     tiles = [z[:, :, b[2]:b[3], b[0]:b[1]] for b in in_bboxes]
     res = [[] for _ in tiles]
-    for step in build_steps(sd, prefix, is_decoder):
+    steps = build_steps(sd, prefix, is_decoder)
+    fixed = estimate_group_norm(sd, steps, fast_mode_thumbnail(z, tile_size), color_fix and not is_decoder) if fast else None
+    norm_idx = -1
+    for step in steps:
         if step[0] == "norm":
+            norm_idx += 1
+            if fixed is not None and fixed[norm_idx] is not None:
+                var, mean = fixed[norm_idx]
+                tiles = [_custom_group_norm(t, mean, var, sd[step[1] + ".weight"], sd[step[1] + ".bias"]) for t in tiles]
+                continue
             stats = [_var_mean(t) for t in tiles]
             pixels = torch.tensor([t.shape[2] * t.shape[3] for t in tiles], dtype=torch.float32)
             pixels = pixels / pixels.max()

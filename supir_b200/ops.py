@@ -410,6 +410,23 @@ def linear_small_m(x, w, bias, out, silu_in=False, silu_out=False, add=None):
     return out
 
 
+def channel_std_mean(x):
+    """(unbiased std, mean) per channel over dims [0, 2, 3] of a contiguous fp32 NCHW tensor — torch.std_mean(x, [0, 2, 3],
+    keepdim=True) — from the deterministic fp64 plane sums of supir_plane_stats; the C-element finalisation stays on the device."""
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
+    N, C = x.shape[:2]
+    planes, hw = N * C, x.shape[2] * x.shape[3]
+    n = int(_native.load().supir_plane_stats_workspace(planes))
+    ws = torch.empty(n, dtype=torch.float64, device=x.device)
+    call("supir_plane_stats", _ptr(x), planes, hw, _ptr(ws), n, _stream())
+    s = ws[:2 * planes].view(N, C, 2).sum(0)
+    cnt = float(N * hw)
+    mean = s[:, 0] / cnt
+    var = (s[:, 1] - s[:, 0] * s[:, 0] / cnt) / (cnt - 1.0)
+    return var.clamp_min(0).sqrt().float().view(1, C, 1, 1), mean.float().view(1, C, 1, 1)
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # text conditioner (textenc.cu)
 # ------------------------------------------------------------------------------------------------------------------

@@ -310,8 +310,56 @@ class _VAENet(nn.Module):
     forward = original_forward
 
     @torch.no_grad()
-    def tiled_forward(self, z, tile_size, shard=False, group=None):
-        """VAEHook.vae_tile_forward with fast_mode=False (tilevae.py:819-970), tiles resident in HBM.
+    def estimate_group_norm(self, z, tile_size, color_fix=False):
+        """Fast mode of the tiled VAE (tilevae.py:855-876 + estimate_group_norm :776-817): the whole input, nearest-exact
+        downsampled to about one tile with its per-channel mean / std restored and clamped to the input's range, runs through
+        the layers as ONE tile; the (mean, biased var) every GroupNorm sees there replace the cross-tile merge. Returns one
+        (mean, var) pair per norm layer — None for the layers after the first downsample when `color_fix` (the reference then
+        estimates only the full-resolution layers and keeps the exact merge for the rest)."""
+        N, C, H, W = z.shape
+        scale = tile_size / max(H, W)
+        iy = nearest_exact_indices(H, scale).to(z.device)
+        ix = nearest_exact_indices(W, scale).to(z.device)
+        small = z.index_select(2, iy).index_select(3, ix).contiguous()          # F.interpolate(mode='nearest-exact'): a gather
+        std_old, mean_old = ops.channel_std_mean(z)
+        std_new, mean_new = ops.channel_std_mean(small)
+        lo, hi = torch.aminmax(z)
+        small = torch.clamp((small - mean_new) / std_new * std_old + mean_old, min=lo, max=hi).contiguous()   # thumbnail-sized
+        pool = self._scratch()
+        self._one = torch.ones(1, dtype=torch.float32, device=z.device)
+        tile = self._start_tile(pool, small)
+        steps = self._fused_steps()
+        n_norm = sum(1 for s_, _ in steps if s_[0] == "norm")
+        fixed = []
+        for step, fuse in steps:
+            if step[0] == "norm":
+                a = tile["h"]
+                n = a.B * 32
+                ws = pool.get((ops.groupnorm_ws_size(a.B, a.HW, a.C),), torch.float64)
+                ops.groupnorm_stats(a.t, a.B, a.HW, ws)
+                mean = torch.empty(n, dtype=torch.float32, device=z.device)
+                var = torch.empty(n, dtype=torch.float32, device=z.device)
+                ops.groupnorm_finalize(ws, n, a.HW * (a.C // 32), mean, var)
+                fixed.append((mean, var))
+                if len(fixed) < n_norm:
+                    tile["fuse_silu"] = fuse
+                    self._norm_apply(pool, step, tile, sums=ws)
+                pool.put(ws)
+                if len(fixed) == n_norm:
+                    break
+            elif color_fix and step[0] == "downsample":
+                break
+            else:
+                self._apply_step(pool, step, tile, fuse)
+        held = [tile["h"].t] + [r for r in tile["res"] if r is not tile["h"].t]
+        pool.put(*held)
+        return fixed + [None] * (n_norm - len(fixed))
+
+    @torch.no_grad()
+    def tiled_forward(self, z, tile_size, shard=False, group=None, fast=False, color_fix=False):
+        """VAEHook.vae_tile_forward (tilevae.py:819-970), tiles resident in HBM. `fast`: the reference's fast mode — GroupNorm
+        statistics estimated once on a thumbnail (estimate_group_norm), every tile then runs independently (no cross-tile
+        merge and, when sharded, no statistics exchange: every rank computes the same estimate).
 
         `shard=True` (opt-in; torch.distributed initialised, identical input on every rank) deals the tiles round-robin over
         the ranks of `group`. Exchanges: per GroupNorm layer ONE all-gather of the per-tile (mean, var) rows (a few KB),
@@ -349,8 +397,16 @@ class _VAENet(nn.Module):
                 wts = pixels / pixels.max()
                 wrows.append(wts / wts.sum())            # GroupNormParam.summary (tilevae.py:629-648)
         wts_all = torch.stack(wrows, 0).to(dev, non_blocking=True) if wrows else None
+        fixed = self.estimate_group_norm(z, tile_size, color_fix and not dec) if fast else None
         norm_idx = 0
         for step, fuse in plan_steps:
+            if step[0] == "norm" and fixed is not None and fixed[norm_idx] is not None:
+                mean, var = fixed[norm_idx]
+                norm_idx += 1
+                for i in mine:
+                    tiles[i]["fuse_silu"] = fuse
+                    self._norm_apply(pool, step, tiles[i], mean=mean, var=var)
+                continue
             if step[0] != "norm":
                 for i in mine:
                     self._apply_step(pool, step, tiles[i], fuse)
@@ -409,6 +465,16 @@ class _VAENet(nn.Module):
         if pool.free_bytes() > POOL_TRIM_BYTES:
             pool.trim()
         return result
+
+
+def nearest_exact_indices(in_size, scale_factor):
+    """Source index of every output pixel of F.interpolate(x, scale_factor=s, mode='nearest-exact') along one axis, computed
+    like ATen does (output size floor(in * s); index min(floor((dst + 0.5) * float32(1 / s)), in - 1))."""
+    import numpy as np
+    out_size = int(math.floor(float(in_size) * scale_factor))
+    scale = np.float32(1.0 / scale_factor)
+    idx = np.floor((np.arange(out_size, dtype=np.float32) + np.float32(0.5)) * scale).astype(np.int64)
+    return torch.from_numpy(np.minimum(idx, in_size - 1))
 
 
 def plan_packed_crops(crops, planes, world):
@@ -540,9 +606,9 @@ class VAEHook:
     """Drop-in for SUPIR.utils.tilevae.VAEHook (tilevae.py:677-700): bound as `net.forward` by init_tile_vae."""
 
     def __init__(self, net, tile_size, is_decoder, fast_decoder=False, fast_encoder=False, color_fix=False, to_gpu=False):
-        if (fast_encoder and not is_decoder) or (fast_decoder and is_decoder):
-            raise NotImplementedError("fast-mode tiled VAE is disabled by SUPIR (SUPIR_model.py:142-150) and not implemented")
         self.net, self.tile_size, self.is_decoder = net, tile_size, is_decoder
+        self.fast_mode = (fast_encoder and not is_decoder) or (fast_decoder and is_decoder)      # tilevae.py:682-683
+        self.color_fix = color_fix and not is_decoder
         self.pad = 11 if is_decoder else 32
         self.shard, self.process_group = False, None      # tile sharding over torch.distributed ranks is opt-in
 
@@ -550,7 +616,8 @@ class VAEHook:
         B, C, H, W = x.shape
         if max(H, W) <= self.pad * 2 + self.tile_size:
             return self.net.original_forward(x)
-        return self.net.tiled_forward(x, self.tile_size, shard=self.shard, group=self.process_group)
+        return self.net.tiled_forward(x, self.tile_size, shard=self.shard, group=self.process_group, fast=self.fast_mode,
+                                      color_fix=self.color_fix)
 
     def split_tiles(self, h, w):
         return split_tiles(h, w, self.tile_size, self.is_decoder)

@@ -249,6 +249,10 @@ def gaussian_latent(moments, eps, scale, z):
     return z
 
 
+def channel_std_mean(x):
+    return torch.std_mean(x, dim=[0, 2, 3], keepdim=True)
+
+
 # ---- text conditioner ----
 def gather_rows_f32(table, idx, out, pos=None, L=0):
     v = table[idx.long().clamp(0, table.shape[0] - 1)]
@@ -336,7 +340,7 @@ _ALL = ["gemm", "conv3x3", "conv_geom", "attention", "attention_1head", "groupno
         "groupnorm_merge_tiles", "groupnorm_apply", "zerosft_apply", "layernorm", "layernorm_stats", "conv3x3_small_cin",
         "conv3x3_small_cout", "conv1x1_small_nchw", "timestep_embedding", "linear_small_m", "upsample2x", "im2col_s2", "f32_to_bf16", "copy2d", "axpy",
         "gaussian_latent", "tile_gather", "tile_blend", "edm_pre", "edm_post", "axpby_f32", "cfg_combine",
-        "gather_rows_f32", "layernorm_f32", "attention_small", "activation"]
+        "gather_rows_f32", "layernorm_f32", "attention_small", "activation", "channel_std_mean"]
 
 
 def install(monkeypatch_or_none=None):

@@ -49,6 +49,28 @@ def test_vae_tiny_untiled_and_tiled_vs_reference():
     assert rel_fro(dec, ovae.decode(sd, z.cpu(), scale_factor=1.0)) <= 3e-2
 
 
+def test_vae_fast_mode_vs_reference():
+    """VAEHook fast mode (tilevae.py:776-817, 855-876: GroupNorm statistics estimated on a thumbnail, tiles independent) against
+    the REFERENCE's fast-mode outputs, incl. the color_fix variant; same tolerance as the exact mode."""
+    from supir_b200 import vae
+    g = np.load(os.path.join(G, "vae_tiny.npz"))
+    gf = np.load(os.path.join(G, "vae_tiny_fast.npz"))
+    with torch.device("cuda"):
+        ae = vae.AutoencoderKLInferenceWrapper(embed_dim=4, ddconfig=json.loads(str(g["cfg"])), lossconfig={"target": "torch.nn.Identity"})
+    ae.load_state_dict(make_state_dict(json.loads(str(g["shapes"])), seed=71), strict=True)
+    big, zbig = randn((1, 3, 192, 160), 83).cuda(), randn((1, 4, 40, 52), 84).cuda()
+    he = vae.VAEHook(ae.encoder, 64, is_decoder=False, fast_encoder=True)
+    hd = vae.VAEHook(ae.decoder, 16, is_decoder=True, fast_decoder=True)
+    hc = vae.VAEHook(ae.encoder, 64, is_decoder=False, fast_encoder=True, color_fix=True)
+    errs = [rel_fro(h(x).cpu(), torch.from_numpy(gf[k])) for h, x, k in ((he, big, "enc_tiled_fast"), (hd, zbig, "dec_tiled_fast"),
+                                                                          (hc, big, "enc_tiled_fast_colorfix"))]
+    print("vae fast mode rel_fro vs reference (enc, dec, enc+color_fix):", ["%.4g" % v for v in errs])
+    assert max(errs) <= 3e-2
+    std, mean = __import__("supir_b200.ops", fromlist=["ops"]).channel_std_mean(big)
+    rs, rm = torch.std_mean(big, dim=[0, 2, 3], keepdim=True)
+    assert torch.allclose(std, rs, rtol=1e-5, atol=1e-6) and torch.allclose(mean, rm, rtol=1e-5, atol=1e-6)
+
+
 def test_vae_repacks_after_a_second_load_state_dict():
     """gradio_demo*.py switch checkpoints with model.load_state_dict(..., strict=False) at run time (gradio_demo_tiled.py:130,134):
     the kernel-layout weights must follow."""

@@ -196,3 +196,18 @@ def test_dpmpp_samplers_toy_network():
     c = {"control": randn((1, 4, 40, 28), 81), "vector": randn((1, 6), 82), "crossattn": randn((1, 3, 5), 83)}
     uc = {"control": c["control"], "vector": randn((1, 6), 84), "crossattn": randn((1, 3, 5), 85)}
     torch.testing.assert_close(smp(toy_network, x, c, uc, control_scale=1.0), torch.from_numpy(g["dpmpp_tiled"]), rtol=1e-5, atol=1e-5)
+
+
+def test_vae_fast_mode_oracle_vs_reference_golden():
+    """VAEHook fast mode (GroupNorm statistics estimated on a thumbnail; tilevae.py:776-817, 855-876), incl. the color_fix
+    variant that estimates only up to the first downsample."""
+    g = np.load(os.path.join(G, "vae_tiny.npz"))
+    gf = np.load(os.path.join(G, "vae_tiny_fast.npz"))
+    sd = make_state_dict(json.loads(str(g["shapes"])), seed=71)
+    big, zbig = randn((1, 3, 192, 160), 83), randn((1, 4, 40, 52), 84)
+    for name, out in (("enc_tiled_fast", ovae.tiled_forward(sd, "encoder.", big, 64, False, fast=True)),
+                      ("dec_tiled_fast", ovae.tiled_forward(sd, "decoder.", zbig, 16, True, fast=True)),
+                      ("enc_tiled_fast_colorfix", ovae.tiled_forward(sd, "encoder.", big, 64, False, fast=True, color_fix=True))):
+        ref = torch.from_numpy(gf[name])
+        assert out.shape == ref.shape
+        assert torch.allclose(out, ref, atol=2e-4, rtol=1e-3), (name, float((out - ref).abs().max()))

@@ -29,6 +29,7 @@ def regen(tmp_path_factory):
         mg.gen_sampler()
         mg.gen_colorfix()
         mg.gen_conditioner()
+        mg.gen_vae_fast()
     finally:
         mg.HERE = saved
     return str(out)
@@ -49,7 +50,7 @@ def test_bookkeeping_and_weights_regenerate_bit_identically(regen):
     _same_npz(os.path.join(regen, "gaussian_weights.npz"), os.path.join(G, "gaussian_weights.npz"))
 
 
-@pytest.mark.parametrize("name", ["zero_modules.npz", "glvcontrol_tiny.npz", "sampler_toy.npz", "colorfix.npz", "conditioner.npz"])
+@pytest.mark.parametrize("name", ["zero_modules.npz", "glvcontrol_tiny.npz", "sampler_toy.npz", "colorfix.npz", "conditioner.npz", "vae_tiny_fast.npz"])
 def test_tensor_fixtures_regenerate_bit_identically(regen, name):
     _same_npz(os.path.join(regen, name), os.path.join(G, name))
 
