@@ -7,7 +7,9 @@ object returned by `create_SUPIR_model` — run unchanged on the B200 backend:
 
     python -c "import supir_b200.compat as c; c.install(); import runpy; runpy.run_path('test.py', run_name='__main__')" ...
 
-SUPIRModel itself (orchestration, text conditioner, colour fix, checkpoint loading) stays the reference's.
+SUPIRModel itself (orchestration, colour fix, checkpoint loading) stays the reference's, and so does the text conditioner
+unless `install(conditioner=True)` also rebinds it to supir_b200.conditioner (same state_dict keys: the SDXL checkpoint's
+`conditioner.embedders.*` weights load into it unchanged).
 """
 import importlib
 
@@ -36,15 +38,32 @@ PATCHES = {
 }
 
 
+# opt-in (install(conditioner=True)): the text conditioner. Off by default: the reference's own classes tokenise with
+# transformers / open_clip and run the towers through those packages; this package's towers take over the arithmetic only.
+CONDITIONER_PATCHES = {
+    "sgm.modules.encoders.modules": {
+        "GeneralConditioner": "supir_b200.conditioner:GeneralConditioner",
+        "GeneralConditionerWithControl": "supir_b200.conditioner:GeneralConditionerWithControl",
+        "FrozenCLIPEmbedder": "supir_b200.conditioner:FrozenCLIPEmbedder",
+        "FrozenOpenCLIPEmbedder2": "supir_b200.conditioner:FrozenOpenCLIPEmbedder2",
+        "ConcatTimestepEmbedderND": "supir_b200.conditioner:ConcatTimestepEmbedderND",
+    },
+    "sgm.modules": {"GeneralConditioner": "supir_b200.conditioner:GeneralConditioner",
+                    "GeneralConditionerWithControl": "supir_b200.conditioner:GeneralConditionerWithControl"},
+}
+
+
 def _resolve(spec):
     mod, attr = spec.split(":")
     return getattr(importlib.import_module(mod), attr)
 
 
-def install(strict=True):
-    """Rebind the reference's hot-path names. Returns the list of (module, attribute) pairs that were patched."""
+def install(strict=True, conditioner=False):
+    """Rebind the reference's hot-path names (and, with conditioner=True, its text conditioner classes). Returns the list of
+    (module, attribute) pairs that were patched."""
     done = []
-    for modname, attrs in PATCHES.items():
+    patches = dict(PATCHES, **CONDITIONER_PATCHES) if conditioner else PATCHES
+    for modname, attrs in patches.items():
         try:
             mod = importlib.import_module(modname)
         except Exception:

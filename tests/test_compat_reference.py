@@ -43,6 +43,27 @@ def test_install_rebinds_reference_targets():
                 setattr(importlib.import_module(modname), a, v)
 
 
+def test_install_conditioner_is_opt_in_and_resolves_through_the_reference_factory():
+    ref_stubs.import_reference()
+    import importlib
+    import sgm.util as sgm_util
+    import supir_b200.compat as compat
+    E = importlib.import_module("sgm.modules.encoders.modules")
+    M = importlib.import_module("sgm.modules")
+    saved = {(m, a): getattr(m, a) for m, attrs in ((E, compat.CONDITIONER_PATCHES["sgm.modules.encoders.modules"]), (M, compat.CONDITIONER_PATCHES["sgm.modules"]))
+             for a in attrs}
+    try:
+        compat.install(strict=False)
+        assert E.FrozenCLIPEmbedder.__module__ == "sgm.modules.encoders.modules"          # untouched by default
+        compat.install(strict=False, conditioner=True)
+        cls = sgm_util.get_obj_from_str("sgm.modules.GeneralConditionerWithControl")
+        assert cls.__module__ == "supir_b200.conditioner"
+        assert sgm_util.get_obj_from_str("sgm.modules.encoders.modules.FrozenOpenCLIPEmbedder2").__module__ == "supir_b200.conditioner"
+    finally:
+        for (m, a), v in saved.items():
+            setattr(m, a, v)
+
+
 def test_reference_still_matches_bookkeeping_fixture():
     import json
     ns = ref_stubs.import_reference()
