@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from . import ops
+from .brownian import BrownianTreeNoiseSampler
 from .config import instantiate_from_config
 
 import itertools
@@ -490,9 +491,10 @@ def get_sigmas_karras(n, sigma_min, sigma_max, rho=7.0, device="cpu"):
 
 
 class BrownianIncrementNoise:
-    """Stand-in for k-diffusion's BrownianTreeNoiseSampler (torchsde): the reference asks it for the normalised Brownian
-    increment between two sigmas, once per step, on disjoint intervals — i.e. independent N(0, I) draws. This class draws
-    them with torch.randn_like (same distribution; NOT the same numbers for a given seed: parity unpinned)."""
+    """Simplest stand-in for k-diffusion's BrownianTreeNoiseSampler: the reference asks it for the normalised Brownian
+    increment between two sigmas, once per step, on disjoint intervals — i.e. independent N(0, I) draws; this class draws
+    them with torch.randn_like. The samplers' default is supir_b200.brownian.BrownianTreeNoiseSampler (one fixed, seeded,
+    query-order-independent Brownian path per run); neither reproduces torchsde's numbers (parity unpinned)."""
 
     def __init__(self, x, sigma_min=None, sigma_max=None):
         self.like = x
@@ -502,7 +504,7 @@ class BrownianIncrementNoise:
 
 
 class RestoreDPMPP2MSampler(BaseDiffusionSampler):
-    noise_sampler_cls = BrownianIncrementNoise
+    noise_sampler_cls = BrownianTreeNoiseSampler        # sampling.py:491-494, 684-687 (k-diffusion's class of the same name)
 
     def __init__(self, s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0, restore_cfg=4.0, restore_cfg_s_tmin=0.05,
                  eta=1.0, *args, **kwargs):

@@ -184,3 +184,19 @@ def test_dpmpp_samplers_match_reference():
         uc = {"control": c["control"], "vector": randn((1, 6), 84), "crossattn": randn((1, 3, 5), 85)}
         out = smp(denoiser, x.cuda(), cond=cu(c), uc=cu(uc), control_scale=1.0).cpu()
         torch.testing.assert_close(out, torch.from_numpy(g["dpmpp_tiled"]), rtol=1e-4, atol=1e-4)
+
+
+def test_brownian_tree_noise_on_the_device():
+    """The DPM++ samplers' default noise source (supir_b200/brownian.py) with CUDA generators: reproducible from the seed,
+    order-independent, unit variance, additive over adjacent intervals (statistics in depth: tests/test_brownian.py)."""
+    from supir_b200.brownian import BrownianTreeNoiseSampler
+    x = torch.zeros(1, 4, 256, 256, device="cuda")
+    a, b = BrownianTreeNoiseSampler(x, 0.0292, 14.6146, seed=11), BrownianTreeNoiseSampler(x, 0.0292, 14.6146, seed=11)
+    sig = [14.6146, 5.0, 1.2, 0.3, 0.0292]
+    fwd = [a(sig[i], sig[i + 1]) for i in range(4)]
+    bwd = [b(sig[i], sig[i + 1]) for i in reversed(range(4))][::-1]
+    assert all(p.is_cuda and torch.equal(p, q) for p, q in zip(fwd, bwd))
+    for z in fwd:
+        assert abs(float(z.var()) - 1) < 0.03 and abs(float(z.mean())) < 0.02
+    w = lambda s0, s1: a(s0, s1) * abs(s1 - s0) ** 0.5  # noqa: E731  un-normalised increment
+    assert torch.allclose(w(5.0, 1.2) + w(1.2, 0.3), w(5.0, 0.3), atol=1e-5)
