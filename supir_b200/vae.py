@@ -622,6 +622,9 @@ class VAEHook:
     def split_tiles(self, h, w):
         return split_tiles(h, w, self.tile_size, self.is_decoder)
 
+    def get_best_tile_size(self, lowerbound, upperbound):
+        return get_best_tile_size(lowerbound, upperbound)
+
 
 class DiagonalGaussianDistribution:
     """distributions.py:24-41; sample() draws eps on the CPU generator like the reference, the arithmetic is a kernel."""

@@ -49,9 +49,13 @@ def test_install_conditioner_is_opt_in_and_resolves_through_the_reference_factor
     import sgm.util as sgm_util
     import supir_b200.compat as compat
     E = importlib.import_module("sgm.modules.encoders.modules")
-    M = importlib.import_module("sgm.modules")
-    saved = {(m, a): getattr(m, a) for m, attrs in ((E, compat.CONDITIONER_PATCHES["sgm.modules.encoders.modules"]), (M, compat.CONDITIONER_PATCHES["sgm.modules"]))
-             for a in attrs}
+    saved = {}
+    for modname, attrs in dict(compat.PATCHES, **compat.CONDITIONER_PATCHES).items():      # install() rebinds all of these
+        try:
+            m = importlib.import_module(modname)
+        except Exception:
+            continue
+        saved.update({(m, a): getattr(m, a) for a in attrs if hasattr(m, a)})
     try:
         compat.install(strict=False)
         assert E.FrozenCLIPEmbedder.__module__ == "sgm.modules.encoders.modules"          # untouched by default
