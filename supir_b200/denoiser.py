@@ -61,6 +61,11 @@ class DiscreteDenoiserWithControl(nn.Module):
         self.register_buffer("sigmas", sigmas)
         self.quantize_c_noise = quantize_c_noise
         self._host_table = sigmas.detach().cpu().numpy().copy()
+        # `sigmas` is a persistent buffer (denoiser.py:43): a checkpoint's `denoiser.sigmas` replaces it, and the host copy follows
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._refresh_host_table())
+
+    def _refresh_host_table(self):
+        self._host_table = self.sigmas.detach().float().cpu().numpy().copy()
 
     def w(self, sigma):
         return self.weighting(sigma)

@@ -79,6 +79,21 @@ def test_product_windows_tiles_and_schedule_match_reference(book):
     assert np.array_equal(sampling.gaussian_weights(16, 24, 2, device="cpu").numpy(), g["w16x24"])
 
 
+def test_denoiser_host_table_follows_a_loaded_sigma_buffer():
+    """`denoiser.sigmas` is a persistent buffer of the reference class (denoiser.py:43): a checkpoint's table replaces the
+    constructed one there, so the host-side copy the fused sampler path quantises against has to follow it."""
+    from supir_b200 import denoiser as dn
+    den = dn.DiscreteDenoiserWithControl(
+        weighting_config={"target": "sgm.modules.diffusionmodules.denoiser_weighting.EpsWeighting"},
+        scaling_config={"target": "sgm.modules.diffusionmodules.denoiser_scaling.EpsScaling"}, num_idx=1000,
+        discretization_config={"target": "sgm.modules.diffusionmodules.discretizer.LegacyDDPMDiscretization"})
+    sq, idx = den.quantize_host(3.0)
+    assert abs(sq - 3.0) < 0.01 and int(den.sigma_to_idx(torch.tensor([3.0]))[0]) == idx
+    den.load_state_dict({"sigmas": den.sigmas * 2})
+    sq2, idx2 = den.quantize_host(3.0)
+    assert idx2 != idx and abs(sq2 - 3.0) < 0.02 and int(den.sigma_to_idx(torch.tensor([3.0]))[0]) == idx2
+
+
 def test_step_constants_match_oracle_arithmetic():
     """The host-side float32 scalars of a step equal what the oracle computes with float32 tensors."""
     from oracle import sampler as osamp
