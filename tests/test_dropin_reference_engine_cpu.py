@@ -153,15 +153,23 @@ def build_reference_engine(RS, cfg, tok_l, tok_g):
     return eng.eval()
 
 
-@pytest.mark.parametrize("tiled", [False, True])
-def test_reference_engine_runs_unchanged_on_the_backend(backend_on_standins, monkeypatch, tiled):
+@pytest.mark.parametrize("mode", ["untiled", "tiled", "tiled_local_prompts"])
+def test_reference_engine_runs_unchanged_on_the_backend(backend_on_standins, monkeypatch, mode):
+    """tiled_local_prompts: one prompt per sampler window, the way gradio_demo_tiled.py calls it (p = [[...]],
+    SUPIR_model.py:163-176 -> a list of conds, sampling.py:623-627)."""
     import contextlib
     import io
     import warnings
     ref_stubs.import_reference()
     from SUPIR.models import SUPIR_model as RS
-    prompts, p_p, n_p = ["a photo of a cat"], ", best quality", "blurry"
-    texts = [prompts[0] + p_p, n_p]
+    tiled = mode != "untiled"
+    p_p, n_p = ", best quality", "blurry"
+    if mode == "tiled_local_prompts":
+        local = ["a cat", "a dog on grass", "sky", "a red brick wall"]          # 24 x 24 latent, tile 16 / stride 8 -> 4 windows
+        prompts, texts = [local], [t + p_p for t in local] + [n_p]
+    else:
+        prompts = ["a photo of a cat"]
+        texts = [prompts[0] + p_p, n_p]
     tok_l = {t: prompt_row(t, 49407) for t in texts}
     tok_g = {t: prompt_row(t, 0) for t in texts}
     target = "sgm.modules.diffusionmodules.sampling." + ("TiledRestoreEDMSampler" if tiled else "RestoreEDMSampler")
@@ -196,6 +204,9 @@ def test_reference_engine_runs_unchanged_on_the_backend(backend_on_standins, mon
                 net.forward.to_gpu = False                      # VAEHook(to_gpu=True) moves the net to devices.get_optimal_device()
         monkeypatch.setattr(torch, "randn_like", SeededNoise(9000))
         want = ref.batchify_sample(img, list(prompts), **kw)
+        # gradio_demo*.py: stage-1 restoration alone through a second denoise encoder (gradio_demo_tiled.py:54, 95)
+        ref.first_stage_model.denoise_encoder_s1 = copy.deepcopy(ref.first_stage_model.denoise_encoder)
+        want_s1 = ref.batchify_denoise(img, is_stage1=True)
     del ref
 
     # ---- 2. the same class, same config + conditioner config, after compat.install(conditioner=True) ----
@@ -216,6 +227,8 @@ def test_reference_engine_runs_unchanged_on_the_backend(backend_on_standins, mon
         monkeypatch.setattr(torch, "randn_like", SeededNoise(9000))
         got = eng.batchify_sample(img, list(prompts), **kw)
         assert type(eng.sampler).__module__ == "supir_b200.sampling"
-    e = rel_fro(got, want)
-    print(f"reference SUPIRModel.batchify_sample on the backend ({'tiled' if tiled else 'untiled'}): rel. Frobenius vs the pure reference {e:.4g}")
-    assert got.shape == want.shape == (1, 3, size, size) and e <= 5e-2
+        eng.first_stage_model.denoise_encoder_s1 = copy.deepcopy(eng.first_stage_model.denoise_encoder)
+        got_s1 = eng.batchify_denoise(img, is_stage1=True)
+    e, e1 = rel_fro(got, want), rel_fro(got_s1, want_s1)
+    print(f"reference SUPIRModel on the backend ({mode}): batchify_sample rel. Frobenius vs the pure reference {e:.4g}, batchify_denoise {e1:.4g}")
+    assert got.shape == want.shape == (1, 3, size, size) and e <= 5e-2 and e1 <= 3e-2
