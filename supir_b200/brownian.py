@@ -61,7 +61,7 @@ class BrownianTree:
             wmid = self._cache.get((level, index))
             if wmid is None:
                 wmid = 0.5 * (wlo + whi) + math.sqrt((hi - lo) / 4.0) * self._normal(level, index)
-                if level <= 12:                          # keep the upper levels (every query crosses them)
+                if level <= 8:                           # keep the upper levels (every query crosses them; <= 8 tensors per path)
                     self._cache[(level, index)] = wmid
             if t == mid:
                 return wmid

@@ -187,3 +187,34 @@ def test_constructors_pick_up_local_pretrained_files(tmp_path):
     g2 = C.FrozenOpenCLIPEmbedder2(arch="ViT-bigG-14", version=str(tmp_path / "open_clip_pytorch_model.bin"), text_cfg=COND_G)
     for k, v in sd.items():
         assert torch.equal(g2.model.state_dict()[k], v), k
+
+
+def test_tokenisation_layouts_with_a_stand_in_bpe():
+    """The two tokenisers' LAYOUT rules around the (absent) BPE vocabulary: HF CLIPTokenizer call arguments and EOT padding for
+    CLIP-L (modules.py:485-494); open_clip.tokenize = [SOT] + ids + [EOT], truncation keeps EOT last, ZERO padding (modules.py:554)."""
+    from supir_b200 import conditioner as C
+
+    class FakeBPE:                                   # one id per word; what transformers.CLIPTokenizer would be asked for
+        def __call__(self, text, add_special_tokens=True, truncation=False, max_length=None, padding=None, return_tensors=None, **kw):
+            if isinstance(text, str):
+                assert add_special_tokens is False
+                return {"input_ids": [1000 + len(w) for w in text.split()]}
+            assert truncation and max_length == 77 and padding == "max_length" and return_tensors == "pt"
+            rows = []
+            for t in text:
+                ids = [C.SOT_TOKEN] + [1000 + len(w) for w in t.split()][:75] + [C.EOT_TOKEN]
+                rows.append(ids + [C.EOT_TOKEN] * (77 - len(ids)))
+            return {"input_ids": torch.tensor(rows)}
+
+    l = C.FrozenCLIPEmbedder(layer="hidden", layer_idx=1, arch=dict(COND_L, layers=2))
+    g = C.FrozenOpenCLIPEmbedder2(arch="ViT-bigG-14", layer="penultimate", legacy=False, always_return_pooled=True, text_cfg=dict(COND_G, layers=2))
+    C._KernelTextEmbedder._tokenizer = FakeBPE()
+    try:
+        tl = l.tokenize(["a cat", "word " * 100])
+        assert tl.shape == (2, 77) and tl[0].tolist()[:5] == [C.SOT_TOKEN, 1001, 1003, C.EOT_TOKEN, C.EOT_TOKEN] and int(tl[1, -1]) == C.EOT_TOKEN
+        tg = g.tokenize(["a cat", "word " * 100])
+        assert tg.shape == (2, 77) and tg[0].tolist()[:6] == [C.SOT_TOKEN, 1001, 1003, C.EOT_TOKEN, 0, 0]
+        assert int(tg[1, 0]) == C.SOT_TOKEN and int(tg[1, -1]) == C.EOT_TOKEN and int((tg[1] == 0).sum()) == 0
+        assert tg.argmax(-1).tolist() == [3, 76]     # the pooling finds EOT as the largest id
+    finally:
+        C._KernelTextEmbedder._tokenizer = None
