@@ -10,9 +10,10 @@ files load unchanged) and `forward()` drives this library's kernels: fp32 residu
 lowers only the matmuls), LayerNorm -> bf16, fused QKV projection on the tcgen05 GEMM, causal attention, out-projection / MLP
 GEMMs with fp32 output accumulated into the stream. There is no torch compute fallback.
 
-Tokenisation is host-side string processing outside this package's scope: the embedders accept token-id tensors directly, or
-strings when a CLIP BPE vocabulary is reachable through `transformers.CLIPTokenizer` at the path the reference configures
-(CKPT_PTH.SDXL_CLIP1_PATH / the `version` argument).
+Tokenisation (host-side string processing) is native too — supir_b200/clip_bpe.py, CLIP's byte-level BPE with the two layouts the
+reference feeds its towers — whenever the vocabulary files are at the path the reference configures (CKPT_PTH.SDXL_CLIP1_PATH /
+the `version` argument: a Hugging Face directory, or open_clip's bpe_simple_vocab_16e6.txt.gz); the embedders also accept
+token-id tensors directly.
 """
 import os
 from collections import OrderedDict
@@ -22,6 +23,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from .clip_bpe import ClipBPE
 from .config import instantiate_from_config
 from .ops import BF16
 
@@ -262,7 +264,9 @@ class AbstractEmbModel(nn.Module):
 
 class _KernelTextEmbedder(AbstractEmbModel):
     """Shared plumbing: lazily packed weights that follow load_state_dict / .to(), a scratch pool, token handling."""
-    _tokenizer = None
+    _tokenizer = None           # transformers.CLIPTokenizer, only when the vocabulary is in a layout clip_bpe does not read
+    _native_bpe = None
+    _bpe_cache = {}
     tokenizer_path = None
 
     def _init_packing(self):
@@ -284,11 +288,18 @@ class _KernelTextEmbedder(AbstractEmbModel):
         for p in self.parameters():
             p.requires_grad = False
 
+    def _bpe(self):
+        """The native CLIP BPE (supir_b200/clip_bpe.py) when its vocabulary files are at `tokenizer_path`, else None."""
+        if self._native_bpe is None and ClipBPE.available(self.tokenizer_path):
+            _KernelTextEmbedder._bpe_cache.setdefault(self.tokenizer_path, ClipBPE.from_path(self.tokenizer_path))
+            self._native_bpe = _KernelTextEmbedder._bpe_cache[self.tokenizer_path]
+        return self._native_bpe
+
     def _hf_tokenizer(self):
         if self._tokenizer is None:
             try:
                 from transformers import CLIPTokenizer
-                type(self)._tokenizer = CLIPTokenizer.from_pretrained(self.tokenizer_path)
+                _KernelTextEmbedder._tokenizer = CLIPTokenizer.from_pretrained(self.tokenizer_path)
             except Exception as e:  # no vocabulary files offline
                 raise RuntimeError(f"no CLIP BPE vocabulary at {self.tokenizer_path!r}: pass token ids (int tensor [B, <= {self.max_length}]) "
                                    "instead of strings") from e
@@ -338,6 +349,8 @@ class FrozenCLIPEmbedder(_KernelTextEmbedder):
 
     def tokenize(self, texts):
         """CLIPTokenizer(..., truncation=True, max_length=77, padding='max_length') (modules.py:485-494): pads with <|endoftext|>."""
+        if self._bpe() is not None:
+            return torch.tensor(self._bpe().tokenize_hf(texts, self.max_length), dtype=torch.long)
         enc = self._hf_tokenizer()(texts, truncation=True, max_length=self.max_length, return_length=True,
                                    return_overflowing_tokens=False, padding="max_length", return_tensors="pt")
         return enc["input_ids"]
@@ -399,6 +412,8 @@ class FrozenOpenCLIPEmbedder2(_KernelTextEmbedder):
 
     def tokenize(self, texts):
         """open_clip.tokenize (modules.py:554): [SOT] + BPE(text) + [EOT], truncated to the context with EOT last, ZERO padded."""
+        if self._bpe() is not None:
+            return torch.tensor(self._bpe().tokenize_open_clip(texts, self.arch["ctx"]), dtype=torch.long)
         tk = self._hf_tokenizer()
         ctx = self.arch["ctx"]
         out = torch.zeros(len(texts), ctx, dtype=torch.long)
