@@ -153,60 +153,68 @@ def build_reference_engine(RS, cfg, tok_l, tok_g):
     return eng.eval()
 
 
-@pytest.mark.parametrize("mode", ["untiled", "tiled", "tiled_local_prompts"])
-def test_reference_engine_runs_unchanged_on_the_backend(backend_on_standins, monkeypatch, mode):
-    """tiled_local_prompts: one prompt per sampler window, the way gradio_demo_tiled.py calls it (p = [[...]],
-    SUPIR_model.py:163-176 -> a list of conds, sampling.py:623-627)."""
+SAMPLING = "sgm.modules.diffusionmodules.sampling."
+P_P, N_P = ", best quality", "blurry"
+LOCAL = ["a cat", "a dog on grass", "sky", "a red brick wall"]          # 24 x 24 latent, tile 16 / stride 8 -> 4 windows
+# (name, sampler target, extra sampler params, tiled VAE, image size, prompts): `tiled_local_prompts` passes one prompt per
+# sampler window, the way gradio_demo_tiled.py does (p = [[...]], SUPIR_model.py:163-176 -> a list of conds, sampling.py:623-627)
+SCENARIOS = [("untiled", "RestoreEDMSampler", None, False, 128, ["a photo of a cat"]),
+             ("tiled", "TiledRestoreEDMSampler", {"tile_size": 16, "tile_stride": 8}, True, 192, ["a photo of a cat"]),
+             ("tiled_local_prompts", "TiledRestoreEDMSampler", {"tile_size": 16, "tile_stride": 8}, True, 192, [LOCAL])]
+KW = dict(num_steps=2, restoration_scale=4.0, s_churn=5, s_noise=1.01, cfg_scale=4.0, seed=77, control_scale=0.9,
+          use_linear_CFG=True, cfg_scale_start=1.0, use_linear_control_scale=True, control_scale_start=0.3)
+
+
+def run_scenarios(eng, monkeypatch, untile_reference_hooks=False):
+    """batchify_sample for every scenario on ONE engine (the sampler is rebuilt per call from `sampler_config`, which test.py /
+    the demos also overwrite between calls), then the stage-1-only path of gradio_demo*.py through a second denoise encoder."""
+    out = {}
+    for name, target, extra, tiled_vae, size, prompts in SCENARIOS:
+        eng.sampler_config = engine_config(SAMPLING + target, False, extra)["sampler_config"]
+        if tiled_vae and not getattr(eng, "_tile_vae_on", False):
+            eng.init_tile_vae(encoder_tile_size=64, decoder_tile_size=8)
+            eng._tile_vae_on = True
+            if untile_reference_hooks:
+                for net in (eng.first_stage_model.denoise_encoder, eng.first_stage_model.encoder, eng.first_stage_model.decoder):
+                    net.forward.to_gpu = False                  # VAEHook(to_gpu=True) moves the net to devices.get_optimal_device()
+        img = (randn((1, 3, size, size), 500) * 0.5).clamp(-1, 1)
+        monkeypatch.setattr(torch, "randn_like", SeededNoise(9000))
+        out[name] = eng.batchify_sample(img, list(prompts), **KW)
+    eng.first_stage_model.denoise_encoder_s1 = copy.deepcopy(eng.first_stage_model.denoise_encoder)
+    out["stage1_denoise"] = eng.batchify_denoise(img, is_stage1=True)       # gradio_demo_tiled.py:54, 95 (tiled hooks in place)
+    return out
+
+
+def test_reference_engine_runs_unchanged_on_the_backend(backend_on_standins, monkeypatch):
     import contextlib
     import io
     import warnings
     ref_stubs.import_reference()
     from SUPIR.models import SUPIR_model as RS
-    tiled = mode != "untiled"
-    p_p, n_p = ", best quality", "blurry"
-    if mode == "tiled_local_prompts":
-        local = ["a cat", "a dog on grass", "sky", "a red brick wall"]          # 24 x 24 latent, tile 16 / stride 8 -> 4 windows
-        prompts, texts = [local], [t + p_p for t in local] + [n_p]
-    else:
-        prompts = ["a photo of a cat"]
-        texts = [prompts[0] + p_p, n_p]
+    texts = ["a photo of a cat" + P_P] + [t + P_P for t in LOCAL] + [N_P]
     tok_l = {t: prompt_row(t, 49407) for t in texts}
     tok_g = {t: prompt_row(t, 0) for t in texts}
-    target = "sgm.modules.diffusionmodules.sampling." + ("TiledRestoreEDMSampler" if tiled else "RestoreEDMSampler")
-    extra = {"tile_size": 16, "tile_stride": 8} if tiled else None
-    size = 192 if tiled else 128
-    img = (randn((1, 3, size, size), 500) * 0.5).clamp(-1, 1)
-    kw = dict(num_steps=2, restoration_scale=4.0, s_churn=5, s_noise=1.01, cfg_scale=4.0, seed=77, control_scale=0.9,
-              use_linear_CFG=True, cfg_scale_start=1.0, use_linear_control_scale=True, control_scale_start=0.3)
     quiet = lambda: contextlib.redirect_stdout(io.StringIO())  # noqa: E731
+    cfg0 = SAMPLING + "RestoreEDMSampler"
 
     # ---- 1. the reference, untouched ----
     import SUPIR.modules.SUPIR_v0 as V
     assert V.GLVControl.__module__ == "SUPIR.modules.SUPIR_v0"
     with quiet(), warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        from sgm.modules.diffusionmodules import sampling as RSAMP
         orig_tensor = torch.tensor
 
         def cpu_tensor(*a, **k):                                # gaussian_weights hard-codes device='cuda' (sampling.py:750)
             k.pop("device", None)
             return orig_tensor(*a, **k)
         monkeypatch.setattr(torch, "tensor", cpu_tensor)
-        ref = build_reference_engine(RS, engine_config(target, False, extra), tok_l, tok_g)
+        ref = build_reference_engine(RS, engine_config(cfg0, False), tok_l, tok_g)
         shapes = {k: list(v.shape) for k, v in ref.state_dict().items()}
         sd = make_state_dict(shapes, seed=123)
         sd["denoiser.sigmas"] = ref.denoiser.sigmas.clone()     # a persistent buffer, not a weight: keep the real sigma table
         ref.load_state_dict(sd)
-        if tiled:
-            ref.init_tile_vae(encoder_tile_size=64, decoder_tile_size=8)
-            import SUPIR.utils.tilevae as TV
-            for net in (ref.first_stage_model.denoise_encoder, ref.first_stage_model.encoder, ref.first_stage_model.decoder):
-                net.forward.to_gpu = False                      # VAEHook(to_gpu=True) moves the net to devices.get_optimal_device()
-        monkeypatch.setattr(torch, "randn_like", SeededNoise(9000))
-        want = ref.batchify_sample(img, list(prompts), **kw)
-        # gradio_demo*.py: stage-1 restoration alone through a second denoise encoder (gradio_demo_tiled.py:54, 95)
-        ref.first_stage_model.denoise_encoder_s1 = copy.deepcopy(ref.first_stage_model.denoise_encoder)
-        want_s1 = ref.batchify_denoise(img, is_stage1=True)
+        want = run_scenarios(ref, monkeypatch, untile_reference_hooks=True)
+        assert type(ref.sampler).__module__ == "sgm.modules.diffusionmodules.sampling"
     del ref
 
     # ---- 2. the same class, same config + conditioner config, after compat.install(conditioner=True) ----
@@ -214,21 +222,16 @@ def test_reference_engine_runs_unchanged_on_the_backend(backend_on_standins, mon
     assert ("SUPIR.modules.SUPIR_v0", "LightGLVUNet") in done and ("sgm.modules", "GeneralConditionerWithControl") in done
     with quiet(), warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        eng = RS.SUPIRModel(**engine_config(target, True, extra)).eval()
+        eng = RS.SUPIRModel(**engine_config(cfg0, True)).eval()
         assert type(eng.model).__module__ == "supir_b200.wrappers" and type(eng.conditioner).__module__ == "supir_b200.conditioner"
         assert type(eng.first_stage_model).__module__ == "supir_b200.vae" and type(eng.denoiser).__module__ == "supir_b200.denoiser"
         assert {k: list(v.shape) for k, v in eng.state_dict().items()} == shapes, "state_dict layout differs from the reference engine's"
         eng.load_state_dict(sd)
         eng.conditioner.embedders[0].tokenize = lambda ts: torch.stack([tok_l[t] for t in ts])
         eng.conditioner.embedders[1].tokenize = lambda ts: torch.stack([tok_g[t] for t in ts])
-        if tiled:
-            eng.init_tile_vae(encoder_tile_size=64, decoder_tile_size=8)
-            assert type(eng.first_stage_model.decoder.forward).__module__ == "supir_b200.vae"
-        monkeypatch.setattr(torch, "randn_like", SeededNoise(9000))
-        got = eng.batchify_sample(img, list(prompts), **kw)
-        assert type(eng.sampler).__module__ == "supir_b200.sampling"
-        eng.first_stage_model.denoise_encoder_s1 = copy.deepcopy(eng.first_stage_model.denoise_encoder)
-        got_s1 = eng.batchify_denoise(img, is_stage1=True)
-    e, e1 = rel_fro(got, want), rel_fro(got_s1, want_s1)
-    print(f"reference SUPIRModel on the backend ({mode}): batchify_sample rel. Frobenius vs the pure reference {e:.4g}, batchify_denoise {e1:.4g}")
-    assert got.shape == want.shape == (1, 3, size, size) and e <= 5e-2 and e1 <= 3e-2
+        got = run_scenarios(eng, monkeypatch)
+        assert type(eng.sampler).__module__ == "supir_b200.sampling" and type(eng.first_stage_model.decoder.forward).__module__ == "supir_b200.vae"
+    errs = {k: rel_fro(got[k], want[k]) for k in want}
+    print("reference SUPIRModel on the backend, rel. Frobenius vs the pure reference:", {k: f"{v:.4g}" for k, v in errs.items()})
+    for k, v in errs.items():
+        assert got[k].shape == want[k].shape and v <= (3e-2 if k == "stage1_denoise" else 5e-2), (k, v)
