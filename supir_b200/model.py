@@ -144,10 +144,13 @@ class SUPIRModel(nn.Module):
         text conditioner when given; 'control' is filled in here like prepare_condition does."""
         assert color_fix_type in ["Wavelet", "AdaIn", "None"]
         N = len(x)
+        if c is None:
+            assert p is not None and len(x) == len(p), "one prompt per image (SUPIR_model.py:86), or pass c= / uc="
         if num_samples > 1:
             assert N == 1
             N = num_samples
             x = x.repeat(N, 1, 1, 1)
+            p = p * N if p is not None else p            # SUPIR_model.py:94
         self.sampler = self.make_sampler(num_steps, restoration_scale, s_churn, s_noise, cfg_scale, use_linear_CFG, cfg_scale_start)
         if seed == -1:
             seed = random.randint(0, 65535)
