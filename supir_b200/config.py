@@ -49,8 +49,32 @@ def instantiate_from_config(config):
     return get_obj_from_str(config["target"])(**dict(config.get("params", dict()) or {}))
 
 
-def load_yaml(path):
-    """options/*.yaml as plain dicts (OmegaConf is not required)."""
+class AttrDict(dict):
+    """Nested-dict view with attribute access, enough of OmegaConf's DictConfig for what the reference's callers do with a
+    loaded options/*.yaml (`config.model`, `config.SDXL_CKPT`, `default_setting.s_cfg_Quality`, and SUPIRModel's
+    `sampler_config.params.num_steps = ...`)."""
+
+    def __getattr__(self, key):
+        try:
+            return self[key]
+        except KeyError as e:
+            raise AttributeError(key) from e
+
+    def __setattr__(self, key, value):
+        self[key] = value
+
+
+def attrify(obj):
+    if isinstance(obj, dict):
+        return AttrDict({k: attrify(v) for k, v in obj.items()})
+    if isinstance(obj, (list, tuple)):
+        return [attrify(v) for v in obj]
+    return obj
+
+
+def load_yaml(path, attr_access=False):
+    """options/*.yaml as plain dicts (OmegaConf is not required); attr_access=True wraps them in AttrDict."""
     import yaml
     with open(path) as f:
-        return yaml.safe_load(f)
+        cfg = yaml.safe_load(f)
+    return attrify(cfg) if attr_access else cfg
