@@ -75,3 +75,29 @@ def test_reference_still_matches_bookkeeping_fixture():
         book = json.load(f)
     for case in book["sliding_windows"]:
         assert [list(c) for c in ns.sampling._sliding_windows(*case["args"])] == case["windows"]
+
+
+def test_every_reference_yaml_instantiates_through_this_packages_factory():
+    """options/SUPIR_v0.yaml, SUPIR_v0_tiled.yaml and SUPIR_v0_Juggernautv9_lightning.yaml, unedited: every `target:` string of the
+    model section — engine, wrapper, denoiser, both networks, VAE, sampler + guider, the conditioner with both text towers at
+    full size — resolves to this package's classes (built on the meta device: 4.8 B parameters cost nothing)."""
+    import glob
+    import torch
+    from supir_b200.config import instantiate_from_config, load_yaml
+    paths = sorted(glob.glob(os.path.join(ref_stubs.REFERENCE_ROOT, "options", "*.yaml")))
+    assert len(paths) >= 3
+    samplers = set()
+    for path in paths:
+        cfg = load_yaml(path, attr_access=True)
+        with torch.device("meta"):
+            m = instantiate_from_config(cfg.model)
+        mods = {type(x).__module__ for x in (m, m.model, m.model.diffusion_model, m.model.control_model, m.denoiser, m.sampler, m.sampler.guider,
+                                             m.first_stage_model, m.conditioner, *m.conditioner.embedders)}
+        assert all(x.startswith("supir_b200.") for x in mods), (path, mods)
+        keys = m.state_dict().keys()
+        assert sum(k.startswith("conditioner.embedders.0.transformer.text_model.encoder.layers.") for k in keys) == 12 * 16
+        assert sum(k.startswith("conditioner.embedders.1.model.transformer.resblocks.") for k in keys) == 32 * 12
+        assert sum(p.numel() for p in m.model.parameters()) > 3.8e9
+        assert cfg.SDXL_CKPT and cfg.default_setting is not None
+        samplers.add(type(m.sampler).__name__)
+    assert samplers == {"RestoreEDMSampler", "TiledRestoreEDMSampler", "RestoreDPMPP2MSampler"}
