@@ -98,6 +98,6 @@ def test_every_reference_yaml_instantiates_through_this_packages_factory():
         assert sum(k.startswith("conditioner.embedders.0.transformer.text_model.encoder.layers.") for k in keys) == 12 * 16
         assert sum(k.startswith("conditioner.embedders.1.model.transformer.resblocks.") for k in keys) == 32 * 12
         assert sum(p.numel() for p in m.model.parameters()) > 3.8e9
-        assert cfg.SDXL_CKPT and cfg.default_setting is not None
+        assert cfg.SDXL_CKPT and cfg.SUPIR_CKPT_Q
         samplers.add(type(m.sampler).__name__)
     assert samplers == {"RestoreEDMSampler", "TiledRestoreEDMSampler", "RestoreDPMPP2MSampler"}
