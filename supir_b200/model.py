@@ -125,6 +125,17 @@ class SUPIRModel(nn.Module):
             return self.conditioner.get_unconditional_conditioning(batch, batch_uc)
         # local prompts: one conditioning per sampler window (SUPIR_model.py:163-176)
         assert len(p) == 1, "Support bs=1 only for local prompt conditioning."
+        from .conditioner import GeneralConditioner
+        if isinstance(self.conditioner, GeneralConditioner) and N == 1:
+            # this package's conditioner treats batch rows independently: ALL window prompts go through the text towers as one
+            # batch (225 windows at 8192^2: one pass instead of the reference's 225 x 2), then split into the per-window list
+            T = len(p[0])
+            rows = lambda v: v.repeat(T, *([1] * (v.dim() - 1)))  # noqa: E731
+            batch_t = {k: (rows(v) if torch.is_tensor(v) and k != "control" else v) for k, v in batch.items()}
+            batch_t["txt"] = ["".join([p_tile, p_p]) for p_tile in p[0]]
+            c_all, uc = self.conditioner.get_unconditional_conditioning(batch_t, batch_uc)
+            c = [dict({k: v[i:i + 1] for k, v in c_all.items() if k != "control"}, control=_z) for i in range(T)]
+            return c, uc
         c, uc = [], None
         for i, p_tile in enumerate(p[0]):
             batch["txt"] = ["".join([p_tile, p_p])]

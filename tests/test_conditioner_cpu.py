@@ -162,8 +162,14 @@ def test_engine_prepare_condition_uses_the_conditioner(cpu_kernels):
     assert seen[0] == ["a photo of a cat, best quality", "an oil painting, best quality"] and seen[2] == ["blurry", "blurry"]
     assert c["crossattn"].shape == (2, 77, COND_L["width"] + COND_G["width"]) and c["vector"].shape == (2, COND_G["proj"] + 3 * 512)
     assert c["control"] is z and torch.equal(uc["control"], z)           # the reference deep-copies the batch for uc
-    cl, ucl = eng.prepare_condition(z[:1], [["a photo of a cat", "an oil painting", "blurry"]], "", "blurry", 1)
+    local = ["a photo of a cat", "an oil painting", "blurry"]
+    cl, ucl = eng.prepare_condition(z[:1], [local], "", "blurry", 1)
     assert isinstance(cl, list) and len(cl) == 3 and ucl["crossattn"].shape[0] == 1
+    # the batched pass over all window prompts == the reference's one-call-per-window loop (SUPIR_model.py:163-176)
+    for i, t in enumerate(local):
+        ci, uci = eng.prepare_condition(z[:1], [t], "", "blurry", 1)
+        assert torch.equal(cl[i]["crossattn"], ci["crossattn"]) and torch.equal(cl[i]["vector"], ci["vector"]) and cl[i]["control"] is z[:1] or torch.equal(cl[i]["control"], z[:1])
+        assert torch.equal(ucl["crossattn"], uci["crossattn"]) and torch.equal(ucl["vector"], uci["vector"])
 
 
 def test_constructors_pick_up_local_pretrained_files(tmp_path):
