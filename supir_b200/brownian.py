@@ -61,7 +61,7 @@ class BrownianTree:
             wmid = self._cache.get((level, index))
             if wmid is None:
                 wmid = 0.5 * (wlo + whi) + math.sqrt((hi - lo) / 4.0) * self._normal(level, index)
-                if level <= 8:                           # keep the upper levels (every query crosses them; <= 8 tensors per path)
+                if level <= 4:                           # keep the top of the tree (every query crosses it): at most 31 tensors
                     self._cache[(level, index)] = wmid
             if t == mid:
                 return wmid

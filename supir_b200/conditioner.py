@@ -266,7 +266,8 @@ class _KernelTextEmbedder(AbstractEmbModel):
     """Shared plumbing: lazily packed weights that follow load_state_dict / .to(), a scratch pool, token handling."""
     _tokenizer = None           # transformers.CLIPTokenizer, only when the vocabulary is in a layout clip_bpe does not read
     _native_bpe = None
-    _bpe_cache = {}
+    _bpe_cache = {}             # vocabulary path -> ClipBPE, shared by the embedders that point at the same files
+    _hf_cache = {}              # vocabulary path -> transformers.CLIPTokenizer
     tokenizer_path = None
 
     def _init_packing(self):
@@ -297,12 +298,15 @@ class _KernelTextEmbedder(AbstractEmbModel):
 
     def _hf_tokenizer(self):
         if self._tokenizer is None:
-            try:
-                from transformers import CLIPTokenizer
-                _KernelTextEmbedder._tokenizer = CLIPTokenizer.from_pretrained(self.tokenizer_path)
-            except Exception as e:  # no vocabulary files offline
-                raise RuntimeError(f"no CLIP BPE vocabulary at {self.tokenizer_path!r}: pass token ids (int tensor [B, <= {self.max_length}]) "
-                                   "instead of strings") from e
+            cached = _KernelTextEmbedder._hf_cache.get(self.tokenizer_path)
+            if cached is None:
+                try:
+                    from transformers import CLIPTokenizer
+                    cached = _KernelTextEmbedder._hf_cache[self.tokenizer_path] = CLIPTokenizer.from_pretrained(self.tokenizer_path)
+                except Exception as e:  # no vocabulary files offline
+                    raise RuntimeError(f"no CLIP BPE vocabulary at {self.tokenizer_path!r}: pass token ids (int tensor [B, <= {self.max_length}]) "
+                                       "instead of strings") from e
+            self._tokenizer = cached
         return self._tokenizer
 
     def _tokens(self, text):

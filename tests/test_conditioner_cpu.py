@@ -214,7 +214,7 @@ def test_tokenisation_layouts_with_a_stand_in_bpe():
 
     l = C.FrozenCLIPEmbedder(layer="hidden", layer_idx=1, arch=dict(COND_L, layers=2))
     g = C.FrozenOpenCLIPEmbedder2(arch="ViT-bigG-14", layer="penultimate", legacy=False, always_return_pooled=True, text_cfg=dict(COND_G, layers=2))
-    C._KernelTextEmbedder._tokenizer = FakeBPE()
+    l._tokenizer = g._tokenizer = FakeBPE()
     try:
         tl = l.tokenize(["a cat", "word " * 100])
         assert tl.shape == (2, 77) and tl[0].tolist()[:5] == [C.SOT_TOKEN, 1001, 1003, C.EOT_TOKEN, C.EOT_TOKEN] and int(tl[1, -1]) == C.EOT_TOKEN
@@ -223,4 +223,4 @@ def test_tokenisation_layouts_with_a_stand_in_bpe():
         assert int(tg[1, 0]) == C.SOT_TOKEN and int(tg[1, -1]) == C.EOT_TOKEN and int((tg[1] == 0).sum()) == 0
         assert tg.argmax(-1).tolist() == [3, 76]     # the pooling finds EOT as the largest id
     finally:
-        C._KernelTextEmbedder._tokenizer = None
+        l._tokenizer = g._tokenizer = None
