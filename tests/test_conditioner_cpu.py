@@ -224,3 +224,21 @@ def test_tokenisation_layouts_with_a_stand_in_bpe():
         assert tg.argmax(-1).tolist() == [3, 76]     # the pooling finds EOT as the largest id
     finally:
         l._tokenizer = g._tokenizer = None
+
+
+def test_towers_are_causal_and_row_independent(cpu_kernels):
+    """Size-independent properties of the text towers: a token only influences its own and later positions (causal mask), and
+    a prompt's embedding does not depend on what else is in the batch."""
+    from supir_b200 import conditioner as C
+    _, _, tl, tg = cond_batches()
+    sd = golden_sd()
+    for emb, toks, prefix in ((C.FrozenCLIPEmbedder(layer="hidden", layer_idx=COND_LAYER_IDX, arch=COND_L), tl, "embedders.0."),
+                              (C.FrozenOpenCLIPEmbedder2(arch="ViT-bigG-14", layer="penultimate", legacy=False, text_cfg=COND_G), tg, "embedders.1.")):
+        emb.load_state_dict({k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)})
+        tok = torch.stack(list(toks.values()))
+        base = emb(tok)
+        changed = tok.clone()
+        changed[:, 10] = (changed[:, 10] + 17) % 900 + 1
+        out = emb(changed)
+        assert torch.equal(out[:, :10], base[:, :10]) and not torch.equal(out[:, 10:], base[:, 10:])
+        assert torch.equal(emb(tok[1:2]), base[1:2])
