@@ -19,7 +19,10 @@ import os
 import unicodedata
 from functools import lru_cache
 
-import regex as re
+try:
+    import regex as re          # \p{L} / \p{N} classes: the third-party `regex` module, like OpenAI's simple_tokenizer
+except ImportError as _e:        # only tokenising STRINGS needs it; token-id inputs do not
+    raise ImportError("supir_b200.clip_bpe needs the `regex` package (unicode property classes in CLIP's split pattern)") from _e
 
 SOT, EOT = "<|startoftext|>", "<|endoftext|>"
 PATTERN = re.compile(r"""<\|startoftext\|>|<\|endoftext\|>|'s|'t|'re|'ve|'m|'ll|'d|[\p{L}]+|[\p{N}]|[^\s\p{L}\p{N}]+""", re.IGNORECASE)

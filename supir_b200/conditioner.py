@@ -23,7 +23,6 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .clip_bpe import ClipBPE
 from .config import instantiate_from_config
 from .ops import BF16
 
@@ -291,9 +290,12 @@ class _KernelTextEmbedder(AbstractEmbModel):
 
     def _bpe(self):
         """The native CLIP BPE (supir_b200/clip_bpe.py) when its vocabulary files are at `tokenizer_path`, else None."""
-        if self._native_bpe is None and ClipBPE.available(self.tokenizer_path):
-            _KernelTextEmbedder._bpe_cache.setdefault(self.tokenizer_path, ClipBPE.from_path(self.tokenizer_path))
-            self._native_bpe = _KernelTextEmbedder._bpe_cache[self.tokenizer_path]
+        if self._native_bpe is None and isinstance(self.tokenizer_path, str) and os.path.exists(self.tokenizer_path):
+            from .clip_bpe import ClipBPE          # imported on first use: only tokenising strings needs the `regex` package
+            if ClipBPE.available(self.tokenizer_path):
+                if self.tokenizer_path not in _KernelTextEmbedder._bpe_cache:
+                    _KernelTextEmbedder._bpe_cache[self.tokenizer_path] = ClipBPE.from_path(self.tokenizer_path)
+                self._native_bpe = _KernelTextEmbedder._bpe_cache[self.tokenizer_path]
         return self._native_bpe
 
     def _hf_tokenizer(self):
