@@ -35,6 +35,28 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert lib.supir_last_error() is not None
 
 
+def test_text_conditioner_entry_points_reject_bad_arguments_before_any_launch():
+    """Argument validation of the textenc.cu entry points (no GPU needed: they return before touching the device) — the error
+    convention of the boundary: negative return code + supir_last_error(), turned into SupirNativeError by the binding."""
+    import ctypes
+    from supir_b200 import _native
+    lib = _native.load()
+    p = ctypes.c_void_p(64)            # a non-null, aligned dummy pointer; never dereferenced on these paths
+    cases = [("supir_attention_small_bf16", (p, 768, p, 768, p, 768, p, 768, 2, 12, 77, 32, 0.125, 1, None), "head_dim"),
+             ("supir_attention_small_bf16", (p, 768, p, 768, p, 768, p, 768, 2, 12, 200, 64, 0.125, 1, None), "tokens"),
+             ("supir_activation_bf16", (p, 64, p, 64, 4, 64, 7, None), "mode"),
+             ("supir_gather_rows_f32", (p, 6, 10, p, None, 0, 0, p, 6, 4, 6, None), "multiples of 4"),
+             ("supir_layernorm_f32", (p, 64, None, 0, None, 0, 4, 64, p, p, 1e-5, None), "bad args")]
+    for name, args, needle in cases:
+        assert getattr(lib, name)(*args) < 0, name
+        assert needle in lib.supir_last_error().decode(), (name, lib.supir_last_error())
+        with pytest.raises(_native.SupirNativeError):
+            _native.call(name, *args)
+    from supir_b200 import ops
+    with pytest.raises(_native.SupirNativeError):
+        ops.attention_small(*(torch.zeros(77, 64, dtype=torch.bfloat16),) * 4, 1, 1, 77)      # CPU tensors: no fallback
+
+
 def test_no_cpu_fallback():
     from supir_b200 import _native, ops
     with pytest.raises(_native.SupirNativeError):
