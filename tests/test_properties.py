@@ -123,3 +123,18 @@ def test_49_windows_over_8_ranks():
     """The generic (foreign-denoiser) path still shards whole windows: seven on ranks 0-6, rank 7 only in the exchange."""
     spans = [sampling.shard_windows(49, 8, r) for r in range(8)]
     assert [hi - lo for _, lo, hi in spans] == [7] * 7 + [0] and spans[0][0] == 7
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.integers(1, 9000), st.integers(8, 2048))
+def test_nearest_exact_indices_match_aten(size, tile):
+    """The gather indices of the fast tiled-VAE mode's thumbnail (vae.nearest_exact_indices) == the pixels ATen's
+    F.interpolate(scale_factor=tile / size, mode='nearest-exact') picks, for every image size / tile size (tilevae.py:859-861)."""
+    import torch.nn.functional as F
+    if size <= tile:                      # the hook only tiles images larger than one padded tile: scale < 1
+        return
+    scale = tile / size
+    x = torch.arange(size, dtype=torch.float32).view(1, 1, 1, size)
+    want = F.interpolate(x, scale_factor=(1.0, scale), mode="nearest-exact")[0, 0, 0].long()
+    got = vae.nearest_exact_indices(size, scale)
+    assert got.shape == want.shape and torch.equal(got, want), (size, tile)
