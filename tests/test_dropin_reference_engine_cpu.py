@@ -3,7 +3,7 @@
 same weights — once as is (pure PyTorch reference), once after `supir_b200.compat.install(conditioner=True)` so that every
 `target:` string resolves to this package's classes — and `batchify_sample(image, prompts, ...)` is run on both: stage-1
 encode / decode, re-encode, text conditioning from prompt strings, the EDM restore sampler driving the reference's opaque denoiser
-lambda (SUPIR_model.py:123-125), final decode, also with the tiled VAE hooks (`init_tile_vae`) and the tiled sampler.
+lambda (SUPIR_model.py:123-125), final decode, also with the tiled VAE hooks (`init_tile_vae`), the tiled sampler and per-window prompts.
 No GPU here, so the backend's kernels are the plain-torch stand-ins of tests/cpu_ops.py (bf16 storage where the kernels store
 bf16): what this pins is that the reference's orchestration code runs UNCHANGED on the backend's classes — constructor
 signatures, attributes it pokes (`model.dtype`, `load_control_model`, re-bindable `.forward` / `.original_forward`,
@@ -159,7 +159,6 @@ LOCAL = ["a cat", "a dog on grass", "sky", "a red brick wall"]          # 24 x 2
 # (name, sampler target, extra sampler params, tiled VAE, image size, prompts): `tiled_local_prompts` passes one prompt per
 # sampler window, the way gradio_demo_tiled.py does (p = [[...]], SUPIR_model.py:163-176 -> a list of conds, sampling.py:623-627)
 SCENARIOS = [("untiled", "RestoreEDMSampler", None, False, 128, ["a photo of a cat"]),
-             ("tiled", "TiledRestoreEDMSampler", {"tile_size": 16, "tile_stride": 8}, True, 192, ["a photo of a cat"]),
              ("tiled_local_prompts", "TiledRestoreEDMSampler", {"tile_size": 16, "tile_stride": 8}, True, 192, [LOCAL])]
 KW = dict(num_steps=2, restoration_scale=4.0, s_churn=5, s_noise=1.01, cfg_scale=4.0, seed=77, control_scale=0.9,
           use_linear_CFG=True, cfg_scale_start=1.0, use_linear_control_scale=True, control_scale_start=0.3)
