@@ -47,6 +47,7 @@ CONDITIONER_PATCHES = {
         "FrozenCLIPEmbedder": "supir_b200.conditioner:FrozenCLIPEmbedder",
         "FrozenOpenCLIPEmbedder2": "supir_b200.conditioner:FrozenOpenCLIPEmbedder2",
         "ConcatTimestepEmbedderND": "supir_b200.conditioner:ConcatTimestepEmbedderND",
+        "PreparedConditioner": "supir_b200.conditioner:PreparedConditioner",
     },
     "sgm.modules": {"GeneralConditioner": "supir_b200.conditioner:GeneralConditioner",
                     "GeneralConditionerWithControl": "supir_b200.conditioner:GeneralConditionerWithControl"},

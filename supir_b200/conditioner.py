@@ -580,3 +580,30 @@ class GeneralConditionerWithControl(GeneralConditioner):
         output = super().forward(batch, force_zero_embeddings)
         output["control"] = batch["control"]
         return output
+
+
+class PreparedConditioner(nn.Module):
+    """modules.py:246-290: conditioning tensors prepared offline (torch.save'd dicts) instead of text towers; rows repeated to the
+    batch of the control latent."""
+
+    def __init__(self, cond_pth, un_cond_pth=None):
+        super().__init__()
+        for k, v in torch.load(cond_pth).items():
+            self.register_buffer(k, v)
+        self.un_cond_pth = un_cond_pth
+        if un_cond_pth is not None:
+            for k, v in torch.load(un_cond_pth).items():
+                self.register_buffer(k + "_uc", v)
+
+    @torch.no_grad()
+    def forward(self, batch, return_uc=False):
+        n = batch["control"].shape[0]
+        output = {}
+        for k, v in self.state_dict().items():
+            if k.endswith("_uc") == bool(return_uc):
+                output[k[:-3] if return_uc else k] = v.detach().clone().repeat(n, *[1 for _ in range(v.ndim - 1)])
+        output["control"] = batch["control"]
+        return output
+
+    def get_unconditional_conditioning(self, batch_c, batch_uc=None, force_uc_zero_embeddings=None):
+        return self(batch_c), (self(batch_c, return_uc=True) if self.un_cond_pth is not None else None)

@@ -27,6 +27,8 @@ _ALIASES = {
     "sgm.models.autoencoder.AutoencoderKL": "supir_b200.vae.AutoencoderKL",
     "sgm.modules.GeneralConditioner": "supir_b200.conditioner.GeneralConditioner",
     "sgm.modules.GeneralConditionerWithControl": "supir_b200.conditioner.GeneralConditionerWithControl",
+    "sgm.modules.PreparedConditioner": "supir_b200.conditioner.PreparedConditioner",
+    "sgm.modules.encoders.modules.PreparedConditioner": "supir_b200.conditioner.PreparedConditioner",
     "sgm.modules.encoders.modules.GeneralConditioner": "supir_b200.conditioner.GeneralConditioner",
     "sgm.modules.encoders.modules.GeneralConditionerWithControl": "supir_b200.conditioner.GeneralConditionerWithControl",
     "sgm.modules.encoders.modules.FrozenCLIPEmbedder": "supir_b200.conditioner.FrozenCLIPEmbedder",

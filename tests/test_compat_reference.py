@@ -101,3 +101,26 @@ def test_every_reference_yaml_instantiates_through_this_packages_factory():
         assert cfg.SDXL_CKPT and cfg.SUPIR_CKPT_Q
         samplers.add(type(m.sampler).__name__)
     assert samplers == {"RestoreEDMSampler", "TiledRestoreEDMSampler", "RestoreDPMPP2MSampler"}
+
+
+def test_prepared_conditioner_matches_the_reference_class(tmp_path):
+    """sgm.modules.PreparedConditioner (modules.py:246-290): conditions loaded from .pth files and repeated to the batch."""
+    import torch
+    ref_stubs.import_reference()
+    import importlib
+    E = importlib.import_module("sgm.modules.encoders.modules")
+    from supir_b200.config import instantiate_from_config
+    g = torch.Generator().manual_seed(0)
+    c = {"crossattn": torch.randn(1, 77, 32, generator=g), "vector": torch.randn(1, 16, generator=g)}
+    uc = {"crossattn": torch.randn(1, 77, 32, generator=g), "vector": torch.randn(1, 16, generator=g)}
+    torch.save(c, tmp_path / "c.pth")
+    torch.save(uc, tmp_path / "uc.pth")
+    batch = {"control": torch.randn(3, 4, 8, 8, generator=g)}
+    for un in (str(tmp_path / "uc.pth"), None):
+        mine = instantiate_from_config({"target": "sgm.modules.PreparedConditioner", "params": {"cond_pth": str(tmp_path / "c.pth"), "un_cond_pth": un}})
+        ref = E.PreparedConditioner(str(tmp_path / "c.pth"), un)
+        assert type(mine).__module__ == "supir_b200.conditioner" and type(ref).__module__ == "sgm.modules.encoders.modules"
+        (a, au), (b, bu) = mine.get_unconditional_conditioning(batch), ref.get_unconditional_conditioning(batch)
+        assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
+        assert (au is None and bu is None) or (au.keys() == bu.keys() and all(torch.equal(au[k], bu[k]) for k in au))
+        assert mine.state_dict().keys() == ref.state_dict().keys()
