@@ -242,3 +242,18 @@ def test_towers_are_causal_and_row_independent(cpu_kernels):
         out = emb(changed)
         assert torch.equal(out[:, :10], base[:, :10]) and not torch.equal(out[:, 10:], base[:, 10:])
         assert torch.equal(emb(tok[1:2]), base[1:2])
+
+
+def test_ucg_rate_semantics(cpu_kernels):
+    """modules.py:155-165, 181-192: an embedder with ucg_rate 1 is always dropped (zeros) in forward(), while
+    get_unconditional_conditioning() switches the dropout off for its two passes and restores the rates afterwards."""
+    batch, batch_uc, tl, tg = cond_batches()
+    gc = build_product_conditioner(tl, tg)
+    full = gc(dict(batch))
+    gc.embedders[0].ucg_rate = 1.0
+    dropped = gc(dict(batch))
+    wl = COND_L["width"]
+    assert float(dropped["crossattn"][..., :wl].abs().max()) == 0.0 and torch.equal(dropped["crossattn"][..., wl:], full["crossattn"][..., wl:])
+    assert torch.equal(dropped["vector"], full["vector"])
+    c, uc = gc.get_unconditional_conditioning(dict(batch), dict(batch_uc))
+    assert torch.equal(c["crossattn"], full["crossattn"]) and gc.embedders[0].ucg_rate == 1.0
