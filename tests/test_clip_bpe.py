@@ -115,3 +115,17 @@ def test_embedders_tokenise_natively_when_the_vocabulary_is_on_disk(trained):
     bpe = clip_bpe.ClipBPE.from_path(path)
     assert torch.equal(l.tokenize(texts), torch.tensor(bpe.tokenize_hf(texts, 77)))
     assert torch.equal(g.tokenize(texts), torch.tensor(bpe.tokenize_open_clip(texts, 77)))
+
+
+def test_fuzz_against_the_tokenizers_backend(trained):
+    """800 random strings over ASCII punctuation, accented Latin, CJK, emoji (with modifiers), all kinds of whitespace, typographic
+    quotes, non-Latin digits, title-case ligatures and combining marks: identical ids ('&' left out: html unescaping differs by
+    design, see above)."""
+    path, vocab, merges, hf = trained
+    mine = clip_bpe.ClipBPE.from_path(path)
+    rng = random.Random(1)
+    pools = ["".join(chr(c) for c in range(32, 127) if chr(c) != "&"), "äöüßéèêñçøåÆ¿¡", "日本語中文한국어", "🙂🚀👍🏽", "\t\n\r\x0b\x0c  ", "’‘“”–—…",
+             "١٢٣४५६", "ǅǈﬁﬀ", "́̈"]
+    for _ in range(800):
+        s = "".join(rng.choice(rng.choice(pools)) for _ in range(rng.randint(0, 40)))
+        assert mine.encode(s) == list(hf(s, add_special_tokens=False)["input_ids"]), repr(s)
