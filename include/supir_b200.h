@@ -7,7 +7,10 @@
  *   - activations are channels-last: images [B, H, W, C] ("NHWC"), tokens [B, L, C] — the same memory;
  *   - bf16 storage unless a name says f32; statistics / softmax / accumulation are fp32 (fp64 for GroupNorm sums);
  *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream and allocates nothing;
- *   - return 0 on success, negative on error; supir_last_error() returns the message (thread-local).
+ *   - return 0 on success, negative on error; supir_last_error() returns the message (thread-local);
+ *   - devices: calls run on the CALLER's current CUDA device (the one the stream belongs to). The intended deployment is one
+ *     process per GPU (torchrun); a process that drives several devices is supported in so far as per-device state (SM count,
+ *     opt-in shared-memory sizes of the large kernels) is cached per device, but the tuning knobs (supir_set_*) are per process.
  */
 #ifndef SUPIR_B200_H
 #define SUPIR_B200_H
