@@ -10,6 +10,7 @@ keys); without a CLIP BPE vocabulary on disk, hand token ids to the embedders or
 import copy
 import random
 
+import numpy as np
 import torch
 import torch.nn as nn
 
@@ -171,7 +172,8 @@ class SUPIRModel(nn.Module):
             dist.broadcast_object_list(box, src=dist.get_global_rank(self._shard_group, 0) if self._shard_group is not None else 0,
                                        group=self._shard_group)
             seed = int(box[0])
-        random.seed(seed)
+        random.seed(seed)                  # pytorch_lightning.seed_everything (SUPIR_model.py:115): python, numpy and torch
+        np.random.seed(seed)
         torch.manual_seed(seed)
         _z = self.encode_first_stage_with_denoise(x, use_sample=False)
         x_stage1 = self.decode_first_stage(_z)
